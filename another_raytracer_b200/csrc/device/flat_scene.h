@@ -1,0 +1,123 @@
+// flat_scene.h — the flattened scene as it lives in HBM. Plain-old-data shared by the host flattener
+// (g++) and the sm_100a kernels (nvcc). See DESIGN.md "Data layout in HBM".
+//
+// The reference's pointer graph (hittable_list / bvh_node / translate / rotate_y / box / primitives /
+// constant_medium, shared_ptr<material>, shared_ptr<texture>) becomes:
+//   prims[]      one fixed-size record per leaf primitive, BVH leaf order first, then media boundaries
+//   nodes[]      one binary BVH over ALL world primitives in WORLD space (instanced primitives keep their
+//                object-space geometry and a transform-chain id; their world boxes bound the transformed
+//                geometry). The closest hit does not depend on the acceleration structure, so this
+//                single tree replaces the reference's list-of-BVHs-of-instances and is bit-compatible
+//                with it as long as the tie-break (dfs_id) and culling rules below are kept.
+//   xforms[]/xform_ops[]  translate / rotate_y chains, outermost first
+//   materials[] / textures[] / images[] + texel atlas / perlins[]
+#ifndef ARTB_FLAT_SCENE_H
+#define ARTB_FLAT_SCENE_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ARTB_ALIGN(n) __align__(n)
+#else
+#define ARTB_ALIGN(n) alignas(n)
+#endif
+
+namespace artb {
+
+enum : uint32_t {
+    PRIM_SPHERE = 0,    // g = cx cy cz r                      sphere.h:39-65
+    PRIM_MSPHERE = 1,   // g = c0(3) c1(3) t0 t1 r             moving_sphere.h:29-58
+    PRIM_RECT_XY = 2,   // g = x0 x1 y0 y1 k                   aarect.cpp:3-19
+    PRIM_RECT_XZ = 3,   // g = x0 x1 z0 z1 k                   aarect.cpp:21-37
+    PRIM_RECT_YZ = 4,   // g = y0 y1 z0 z1 k                   aarect.cpp:39-55
+    PRIM_TRIANGLE = 5,  // g = p1(3) p2(3) p3(3)               triangle.h:22-88
+    PRIM_MEDIUM = 6     // g = neg_inv_density, first boundary prim, boundary prim count, medium slot
+                        //                                      constant_medium.h:37-82
+};
+
+struct ARTB_ALIGN(16) FlatPrim {      // 96 B
+    double g[10];
+    uint32_t type;
+    uint32_t material;
+    uint32_t xform;       // 0 = identity
+    uint32_t dfs_id;      // position in the reference's depth-first test order: reported id + tie-break
+};
+
+// Binary BVH node holding BOTH children's boxes, so one 128-byte fetch decides both descents.
+// child >= 0: internal node index. count > 0: leaf, prims[child .. child+count).
+struct ARTB_ALIGN(16) FlatNode {      // 128 B
+    double lo0[3], hi0[3];
+    double lo1[3], hi1[3];
+    int32_t child0, child1;
+    int32_t count0, count1;
+    int32_t pad[4];
+};
+
+enum : uint32_t { XFORM_TRANSLATE = 0, XFORM_ROTATE_Y = 1 };
+
+struct ARTB_ALIGN(16) FlatXformOp {   // 32 B
+    double a, b, c;       // translate: offset xyz          hittable.cpp:3-12
+                          // rotate_y:  sin_theta, cos_theta hittable.cpp:57-85
+    uint32_t type;
+    uint32_t pad;
+};
+
+struct FlatXform { uint32_t first_op, n_ops; };   // ops are applied first_op .. first_op+n_ops-1 going IN
+
+enum : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4,
+                  MAT_COUNT = 5 };
+
+struct ARTB_ALIGN(16) FlatMaterial {  // 48 B
+    double albedo[3];     // metal only
+    double param;         // metal: fuzz; dielectric: ir
+    uint32_t type;
+    uint32_t texture;     // lambertian / diffuse_light / isotropic
+    uint32_t pad[2];
+};
+
+enum : uint32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3, TEX_BARY_IMAGE = 4, TEX_BARY = 5 };
+
+struct ARTB_ALIGN(16) FlatTexture {   // 96 B
+    double p[9];          // solid: rgb | noise: scale | bary_image: ua va ub vb uc vc | bary: a(3) b(3) c(3)
+    uint32_t type;
+    uint32_t a, b;        // checker: even, odd texture | noise: perlin index | image / bary_image: image index
+    uint32_t pad[3];
+};
+
+struct FlatImage { uint64_t offset; int32_t width, height, bytes_per_pixel, pad; };   // width==0: "no data" => cyan
+
+struct FlatPerlin {       // perlin.h:56-61
+    double ranvec[256][3];
+    int32_t perm_x[256], perm_y[256], perm_z[256];
+};
+
+// device-side view (all pointers are device pointers)
+struct SceneView {
+    const FlatPrim* prims;
+    const FlatNode* nodes;
+    const FlatXformOp* xform_ops;
+    const FlatXform* xforms;
+    const FlatMaterial* materials;
+    const FlatTexture* textures;
+    const FlatImage* images;
+    const unsigned char* texels;
+    const FlatPerlin* perlins;
+    uint32_t n_prims, n_world_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
+    int32_t root_child, root_count;   // when the world has a single leaf: no nodes at all
+    double background[3];
+};
+
+struct CameraParams {     // camera.h:49-56 + engine.h:62-63
+    double origin[3], lower_left_corner[3], horizontal[3], vertical[3], u[3], v[3], w[3];
+    double lens_radius, time0, time1;
+};
+
+// closest-hit record reported by artb_trace_batch and consumed by the shade kernels
+struct ARTB_ALIGN(8) HitRecordOut {
+    double t, p[3], normal[3], u, v;
+    int32_t hit, prim_id, front_face, material_type;
+};
+
+} // namespace artb
+
+#endif

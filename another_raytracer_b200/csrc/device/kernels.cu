@@ -1,0 +1,717 @@
+// kernels.cu — the sm_100a kernels of the wavefront path tracer and the host code that launches them.
+//
+// Pipeline (one "wave" = every live path advances by one bounce), replacing the recursion of
+// engine::_ray_color (engine.h:447-466) and the pixel/sample loops of engine::_run_single (engine.h:58-94):
+//
+//   k_generate   free path slots take the next (pixel, sample): jitter + camera::get_ray -> ray queue
+//   k_extend     closest hit per queued ray (rt_intersect.cuh); misses add the background and free the
+//                slot; hits are binned BY MATERIAL TYPE into per-material queues (warp-aggregated appends)
+//   k_shade      one warp = 32 hits of ONE material type: hit record, texture, emitted, scatter; paths that
+//                end (light, absorbed, depth 50) add their radiance and free the slot, the others queue the
+//                scattered ray for the next wave
+//   k_resolve    write_color (color.h:6-22): mean, gamma 2, clamp, 8-bit
+//
+// Path state lives in HBM as three arrays of sector-sized records indexed by slot (ray 64 B, aux 32 B,
+// hit 16 B), so a queue-indexed gather wastes no bytes of a 32 B sector. No kernel waits on another one;
+// queue counters are reset by two single-thread housekeeping kernels per wave, all on one stream.
+#include "renderer.h"
+#include "rt_shade.cuh"
+
+#include <cstdio>
+#include <stdexcept>
+#include <vector>
+
+namespace artb {
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct __align__(16) PathRay { double o[3], d[3], tm, pad; };                       // 64 B
+struct __align__(16) PathAux { float thr[3]; uint32_t pixel, sample, rng_block, depth, pad; };   // 32 B
+struct __align__(16) PathHit { double t; int32_t prim; int32_t pad; };              // 16 B
+
+struct WaveCounters {
+    uint32_t n_extend[2];
+    uint32_t n_regen[2];
+    uint32_t n_shade[MAT_COUNT];
+    uint32_t cursor;
+    uint32_t n_list;                  // pixels in the current round's list
+    uint32_t n_next_list;             // adaptive: pixels still unconverged
+    unsigned long long issued, total, rays, finished;
+};
+
+struct WaveBuffers {
+    PathRay* rays;
+    PathAux* aux;
+    PathHit* hits;
+    uint32_t* q_extend[2];
+    uint32_t* q_regen[2];
+    uint32_t* q_shade[MAT_COUNT];
+    WaveCounters* c;
+    uint32_t pool;
+};
+
+struct RoundParams {
+    CameraParams cam;
+    int width, height, max_depth;
+    uint32_t seed, stream;
+    uint32_t first_sample;            // per-pixel index of the first sample of this round
+    uint32_t batch;                   // samples per listed pixel in this round
+    const uint32_t* pixel_list;       // nullptr: identity over width*height
+    float* accum;                     // W*H*3 sums
+    uint32_t* count;                  // per-pixel finished samples (adaptive) or nullptr
+    float* lumsq;                     // per-pixel sum of squared sample luminance (adaptive) or nullptr
+};
+
+// ---- small device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ void queue_push(uint32_t* q, uint32_t* count, bool pred, uint32_t value, int lane)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, uint32_t(__popc(m)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ DRay load_ray(const PathRay* rays, uint32_t slot)
+{
+    const double2* p = reinterpret_cast<const double2*>(rays + slot);
+    const double2 a = p[0], b = p[1], c = p[2], d = p[3];
+    DRay r;
+    r.o = mk3(a.x, a.y, b.x);
+    r.d = mk3(b.y, c.x, c.y);
+    r.tm = d.x;
+    return r;
+}
+
+__device__ __forceinline__ void store_ray(PathRay* rays, uint32_t slot, const DRay& r)
+{
+    double2* p = reinterpret_cast<double2*>(rays + slot);
+    p[0] = make_double2(r.o.x, r.o.y);
+    p[1] = make_double2(r.o.z, r.d.x);
+    p[2] = make_double2(r.d.y, r.d.z);
+    p[3] = make_double2(r.tm, 0.0);
+}
+
+__device__ __forceinline__ void add_radiance(const RoundParams& rp, uint32_t pixel, float r, float g, float b)
+{
+    float* a = rp.accum + size_t(pixel) * 3;
+    if (r != 0.f) atomicAdd(a + 0, r);
+    if (g != 0.f) atomicAdd(a + 1, g);
+    if (b != 0.f) atomicAdd(a + 2, b);
+    if (rp.count) {
+        atomicAdd(rp.count + pixel, 1u);
+        const float y = 0.2126f * r + 0.7152f * g + 0.0722f * b;
+        if (y != 0.f) atomicAdd(rp.lumsq + pixel, y * y);
+    }
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------
+__global__ void k_init_pool(WaveBuffers w)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w.pool) w.q_regen[0][i] = i;
+    if (i == 0) {
+        WaveCounters* c = w.c;
+        c->n_extend[0] = c->n_extend[1] = 0;
+        c->n_regen[0] = w.pool; c->n_regen[1] = 0;
+        for (int m = 0; m < MAT_COUNT; ++m) c->n_shade[m] = 0;
+        c->cursor = 0; c->n_list = 0; c->n_next_list = 0;
+        c->issued = c->total = c->rays = c->finished = 0;
+    }
+}
+
+// n_list_fixed >= 0: use it; otherwise take the list length the adaptive update left in n_next_list
+__global__ void k_round_begin(WaveCounters* c, long long n_list_fixed, uint32_t batch)
+{
+    const uint32_t n = n_list_fixed >= 0 ? uint32_t(n_list_fixed) : c->n_next_list;
+    c->n_list = n;
+    c->n_next_list = 0;
+    c->issued = 0;
+    c->total = (unsigned long long)n * batch;
+}
+
+__global__ void __launch_bounds__(256) k_generate(WaveBuffers w, RoundParams rp, int cur)
+{
+    WaveCounters* c = w.c;
+    const uint32_t n = c->n_regen[cur];
+    const unsigned long long issued = c->issued, total = c->total;
+    const uint32_t n_list = c->n_list;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        bool spawned = false;
+        if (valid) {
+            slot = w.q_regen[cur][i];
+            const unsigned long long s = issued + i;
+            if (s < total) {
+                spawned = true;
+                const uint32_t li = uint32_t(s % n_list);
+                const uint32_t k = uint32_t(s / n_list);
+                const uint32_t pixel = rp.pixel_list ? rp.pixel_list[li] : li;
+                const uint32_t sample = rp.first_sample + k;
+                const int px = int(pixel % uint32_t(rp.width)), py = int(pixel / uint32_t(rp.width));
+                Philox g;
+                g.init(rp.seed, rp.stream, pixel, sample, 0, 0);
+                // engine.h:62-63 — row 0 is the top of the image, v is flipped
+                const double u = (px + g.next_double()) / (rp.width - 1);
+                const double v = ((rp.height - 1 - py) + g.next_double()) / (rp.height - 1);
+                const DRay r = camera_ray(rp.cam, u, v, g);
+                store_ray(w.rays, slot, r);
+                PathAux a;
+                a.thr[0] = a.thr[1] = a.thr[2] = 1.f;
+                a.pixel = pixel; a.sample = sample; a.rng_block = g.c2; a.depth = 0; a.pad = 0;
+                *reinterpret_cast<uint4*>(w.aux + slot) = *reinterpret_cast<const uint4*>(&a);
+                *(reinterpret_cast<uint4*>(w.aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
+            }
+        }
+        queue_push(w.q_extend[cur], &c->n_extend[cur], spawned, slot, lane);
+        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], valid && !spawned, slot, lane);
+    }
+}
+
+__global__ void k_after_generate(WaveCounters* c, int cur)
+{
+    const unsigned long long left = c->total - c->issued;
+    const unsigned long long n = c->n_regen[cur];
+    c->issued += n < left ? n : left;
+    c->n_regen[cur] = 0;
+    c->cursor = 0;
+}
+
+__global__ void __launch_bounds__(128) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+{
+    WaveCounters* c = w.c;
+    const uint32_t n = c->n_extend[cur];
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->cursor, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        uint32_t slot = 0;
+        int mat = -1;
+        bool miss = false;
+        if (valid) {
+            slot = w.q_extend[cur][i];
+            const DRay r = load_ray(w.rays, slot);
+            const PathAux* a = w.aux + slot;
+            MediumXi xi;
+            xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
+            xi.path_lo = a->pixel; xi.path_hi = a->sample; xi.bounce = a->depth;
+            const ClosestHit h = closest_hit(s, r, 0.001, INFINITY, xi);
+            if (h.prim < 0) {
+                miss = true;
+                add_radiance(rp, a->pixel, a->thr[0] * float(s.background[0]), a->thr[1] * float(s.background[1]),
+                             a->thr[2] * float(s.background[2]));
+            } else {
+                PathHit ph; ph.t = h.t; ph.prim = h.prim; ph.pad = 0;
+                *reinterpret_cast<double2*>(w.hits + slot) = *reinterpret_cast<const double2*>(&ph);
+                mat = int(s.materials[s.prims[h.prim].material].type);
+            }
+        }
+        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], miss, slot, lane);
+#pragma unroll
+        for (int m = 0; m < MAT_COUNT; ++m) queue_push(w.q_shade[m], &c->n_shade[m], mat == m, slot, lane);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+{
+    WaveCounters* c = w.c;
+    uint32_t start[MAT_COUNT + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int m = 0; m < MAT_COUNT; ++m) start[m + 1] = start[m] + ((c->n_shade[m] + 31u) >> 5);
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < start[MAT_COUNT]; wi += n_warps) {
+        int m = 0;
+#pragma unroll
+        for (int k = 1; k < MAT_COUNT; ++k) if (wi >= start[k]) m = k;
+        const uint32_t i = (wi - start[m]) * 32u + uint32_t(lane);
+        const bool valid = i < c->n_shade[m];
+        uint32_t slot = 0;
+        bool cont = false;
+        if (valid) {
+            slot = w.q_shade[m][i];
+            const DRay r = load_ray(w.rays, slot);
+            PathAux a;
+            *reinterpret_cast<uint4*>(&a) = *reinterpret_cast<const uint4*>(w.aux + slot);
+            *(reinterpret_cast<uint4*>(&a) + 1) = *(reinterpret_cast<const uint4*>(w.aux + slot) + 1);
+            const PathHit ph = w.hits[slot];
+            const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
+            const FlatMaterial& mat = s.materials[h.material];
+            if (mat.type == MAT_DIFFUSE_LIGHT) {
+                const d3 e = material_emitted(s, mat, h);
+                add_radiance(rp, a.pixel, a.thr[0] * float(e.x), a.thr[1] * float(e.y), a.thr[2] * float(e.z));
+            } else {
+                Philox g;
+                g.init(rp.seed, rp.stream, a.pixel, a.sample, a.rng_block, 0);
+                d3 att; DRay sc;
+                const bool ok = material_scatter(s, mat, r, h, g, att, sc);
+                if (ok && a.depth + 1u < uint32_t(rp.max_depth)) {
+                    cont = true;
+                    store_ray(w.rays, slot, sc);
+                    a.thr[0] *= float(att.x); a.thr[1] *= float(att.y); a.thr[2] *= float(att.z);
+                    a.depth += 1; a.rng_block = g.c2;
+                    *reinterpret_cast<uint4*>(w.aux + slot) = *reinterpret_cast<const uint4*>(&a);
+                    *(reinterpret_cast<uint4*>(w.aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
+                } else {
+                    add_radiance(rp, a.pixel, 0.f, 0.f, 0.f);   // absorbed / depth limit: a black sample (engine.h:451-452, 462-463)
+                }
+            }
+        }
+        queue_push(w.q_extend[cur ^ 1], &c->n_extend[cur ^ 1], cont, slot, lane);
+        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], valid && !cont, slot, lane);
+    }
+}
+
+__global__ void k_after_shade(WaveCounters* c, int cur)
+{
+    c->rays += c->n_extend[cur];
+    c->n_extend[cur] = 0;
+    for (int m = 0; m < MAT_COUNT; ++m) c->n_shade[m] = 0;
+
+}
+
+// adaptive variance mask: keep the pixels of the current list whose luminance mean is not yet settled
+__global__ void k_adaptive_update(WaveCounters* c, const uint32_t* list, uint32_t* next_list, const float* accum,
+                                  const uint32_t* count, const float* lumsq, uint32_t min_spp, uint32_t max_spp,
+                                  float threshold)
+{
+    const uint32_t n = c->n_list;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
+        const uint32_t i = base + lane;
+        bool keep = false;
+        uint32_t pixel = 0;
+        if (i < n) {
+            pixel = list ? list[i] : i;
+            const uint32_t cnt = count[pixel];
+            if (cnt < max_spp) {
+                keep = true;
+                if (cnt >= min_spp && cnt > 1) {
+                    const float* a = accum + size_t(pixel) * 3;
+                    const float mean = (0.2126f * a[0] + 0.7152f * a[1] + 0.0722f * a[2]) / float(cnt);
+                    const float var = fmaxf(lumsq[pixel] / float(cnt) - mean * mean, 0.f) * float(cnt) / float(cnt - 1);
+                    const float se = sqrtf(var / float(cnt));
+                    keep = se > threshold * (mean + 0.05f);
+                }
+            }
+        }
+        queue_push(next_list, &c->n_next_list, keep, pixel, lane);
+    }
+}
+
+__global__ void k_resolve(const float* accum, const uint32_t* count, int n_pixels, int fixed_spp, uint8_t* rgb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const double n = fixed_spp > 0 ? double(fixed_spp) : double(count[i] > 0 ? count[i] : 1u);
+    const double scale = 1.0 / n;                          // color.h:12-21
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double v = sqrt(scale * double(accum[size_t(i) * 3 + k]));
+        v = v < 0.0 ? 0.0 : (v > 0.999 ? 0.999 : v);
+        rgb[size_t(i) * 3 + k] = uint8_t(256 * v);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* rays, uint64_t n, double t_min, double t_max,
+                                                     const double* xi, HitRecordOut* out)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DRay r;
+    r.o = ld3(rays + i * 7); r.d = ld3(rays + i * 7 + 3); r.tm = rays[i * 7 + 6];
+    MediumXi mx;
+    mx.row = xi ? xi + i * s.n_media : nullptr;
+    mx.seed = 0; mx.stream = 0; mx.path_lo = uint32_t(i); mx.path_hi = uint32_t(i >> 32); mx.bounce = 0;
+    const ClosestHit h = closest_hit(s, r, t_min, t_max, mx);
+    HitRecordOut o;
+    if (h.prim < 0) {
+        o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
+        o.t = o.u = o.v = 0; o.p[0] = o.p[1] = o.p[2] = 0; o.normal[0] = o.normal[1] = o.normal[2] = 0;
+    } else {
+        const HitInfo hi = make_hit_info(s, h.prim, r, h.t);
+        o.hit = 1; o.prim_id = int32_t(h.dfs); o.front_face = hi.front_face ? 1 : 0;
+        o.material_type = int32_t(s.materials[hi.material].type);
+        o.t = hi.t; o.u = hi.u; o.v = hi.v;
+        o.p[0] = hi.p.x; o.p[1] = hi.p.y; o.p[2] = hi.p.z;
+        o.normal[0] = hi.normal.x; o.normal[1] = hi.normal.y; o.normal[2] = hi.normal.z;
+    }
+    out[i] = o;
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct Renderer::Impl {
+    // scene arrays
+    std::vector<void*> scene_allocs;
+    // wave buffers
+    WaveBuffers wb{};
+    std::vector<void*> pool_allocs;
+    WaveCounters* counters_host = nullptr;      // pinned
+    int sm_count = 148;
+    // adaptive scratch
+    uint32_t* list[2] = { nullptr, nullptr };
+    uint32_t* tile_list = nullptr;
+    float* lumsq = nullptr;
+    size_t list_capacity = 0;
+    // event pool for per-kernel timing
+    std::vector<cudaEvent_t> ev;
+};
+
+template <class T>
+static T* dev_alloc(std::vector<void*>& bag, size_t n)
+{
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    bag.push_back(p);
+    return static_cast<T*>(p);
+}
+
+template <class T>
+static const T* dev_upload(std::vector<void*>& bag, const std::vector<T>& v, cudaStream_t st, uint64_t& bytes)
+{
+    T* p = dev_alloc<T>(bag, v.size());
+    if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    bytes += v.size() * sizeof(T);
+    return p;
+}
+
+Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(device)
+{
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        delete impl_;
+        throw std::runtime_error("no CUDA device: this backend has no CPU fallback");
+    }
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    impl_->sm_count = prop.multiProcessorCount;
+    cudaStream_t st;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    stream_ = st;
+
+    if (pool_paths == 0) pool_paths = 1u << 21;
+    pool_paths = (pool_paths + 31u) & ~31u;
+    WaveBuffers& w = impl_->wb;
+    w.pool = pool_paths;
+    w.rays = dev_alloc<PathRay>(impl_->pool_allocs, pool_paths);
+    w.aux = dev_alloc<PathAux>(impl_->pool_allocs, pool_paths);
+    w.hits = dev_alloc<PathHit>(impl_->pool_allocs, pool_paths);
+    for (int k = 0; k < 2; ++k) {
+        w.q_extend[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
+        w.q_regen[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
+    }
+    for (int m = 0; m < MAT_COUNT; ++m) w.q_shade[m] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
+    w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
+    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
+}
+
+Renderer::~Renderer()
+{
+    cudaSetDevice(device_);
+    cudaDeviceSynchronize();
+    for (void* p : impl_->scene_allocs) cudaFree(p);
+    for (void* p : impl_->pool_allocs) cudaFree(p);
+    if (impl_->list[0]) cudaFree(impl_->list[0]);
+    if (impl_->list[1]) cudaFree(impl_->list[1]);
+    if (impl_->tile_list) cudaFree(impl_->tile_list);
+    if (impl_->lumsq) cudaFree(impl_->lumsq);
+    if (impl_->counters_host) cudaFreeHost(impl_->counters_host);
+    for (cudaEvent_t e : impl_->ev) cudaEventDestroy(e);
+    if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+    delete impl_;
+}
+
+void Renderer::upload(const FlatScene& fs)
+{
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (void* p : impl_->scene_allocs) cudaFree(p);
+    impl_->scene_allocs.clear();
+    if (fs.bvh_depth >= ARTB_STACK_DEPTH - 1)
+        throw std::runtime_error("scene BVH is deeper than the device traversal stack");
+    uint64_t bytes = 0;
+    SceneView v{};
+    v.prims = dev_upload(impl_->scene_allocs, fs.prims, st, bytes);
+    v.nodes = dev_upload(impl_->scene_allocs, fs.nodes, st, bytes);
+    v.xform_ops = dev_upload(impl_->scene_allocs, fs.xform_ops, st, bytes);
+    v.xforms = dev_upload(impl_->scene_allocs, fs.xforms, st, bytes);
+    v.materials = dev_upload(impl_->scene_allocs, fs.materials, st, bytes);
+    v.textures = dev_upload(impl_->scene_allocs, fs.textures, st, bytes);
+    v.images = dev_upload(impl_->scene_allocs, fs.images, st, bytes);
+    v.texels = dev_upload(impl_->scene_allocs, fs.texels, st, bytes);
+    v.perlins = dev_upload(impl_->scene_allocs, fs.perlins, st, bytes);
+    v.n_prims = uint32_t(fs.prims.size());
+    v.n_world_prims = fs.n_world_prims;
+    v.n_nodes = uint32_t(fs.nodes.size());
+    v.n_media = fs.n_media;
+    v.n_xforms = uint32_t(fs.xforms.size());
+    v.n_materials = uint32_t(fs.materials.size());
+    v.n_textures = uint32_t(fs.textures.size());
+    v.root_child = fs.root_child;
+    v.root_count = fs.root_count;
+    for (int k = 0; k < 3; ++k) v.background[k] = fs.background[k];
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    view_ = v;
+    scene_bytes_ = bytes;
+    has_scene_ = true;
+}
+
+float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_min, double t_max, const double* xi_dev,
+                                   HitRecordOut* out_dev)
+{
+    if (!has_scene_) throw std::runtime_error("trace_batch: no scene uploaded");
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0.f;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    const unsigned blocks = unsigned((n + 127) / 128);
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    k_trace_batch<<<blocks, 128, 0, st>>>(view_, rays_dev, n, t_min, t_max, xi_dev, out_dev);
+    CUDA_CHECK(cudaEventRecord(e1, st));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
+}
+
+void Renderer::trace_batch(const double* rays_host, uint64_t n, double t_min, double t_max, const double* xi_host,
+                           HitRecordOut* out_host)
+{
+    if (!has_scene_) throw std::runtime_error("trace_batch: no scene uploaded");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    std::vector<void*> bag;
+    try {
+        double* d_rays = dev_alloc<double>(bag, n * 7);
+        HitRecordOut* d_out = dev_alloc<HitRecordOut>(bag, n);
+        double* d_xi = nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(d_rays, rays_host, n * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+        if (xi_host && view_.n_media) {
+            d_xi = dev_alloc<double>(bag, n * view_.n_media);
+            CUDA_CHECK(cudaMemcpyAsync(d_xi, xi_host, n * view_.n_media * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        trace_batch_device(d_rays, n, t_min, t_max, d_xi, d_out);
+        CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, n * sizeof(HitRecordOut), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (...) {
+        for (void* p : bag) cudaFree(p);
+        throw;
+    }
+    for (void* p : bag) cudaFree(p);
+}
+
+void Renderer::resolve_device(const float* accum_dev, const uint32_t* count_dev, int n_pixels, int fixed_spp, uint8_t* rgb_dev)
+{
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    k_resolve<<<(n_pixels + 255) / 256, 256, 0, st>>>(accum_dev, count_dev, n_pixels, fixed_spp, rgb_dev);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+void Renderer::render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
+                             RenderStats* stats, bool profile)
+{
+    if (!has_scene_) throw std::runtime_error("render: no scene uploaded");
+    if (p.width < 2 || p.height < 2 || p.samples_per_pixel < 1 || p.max_depth < 1)
+        throw std::runtime_error("render: bad image size / spp / depth");
+    if (p.adaptive && !count_dev) throw std::runtime_error("render: adaptive mode needs a count buffer");
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    Impl& I = *impl_;
+    WaveBuffers& w = I.wb;
+    const size_t n_pixels = size_t(p.width) * size_t(p.height);
+
+    // scratch for pixel lists
+    if (I.list_capacity < n_pixels) {
+        for (int k = 0; k < 2; ++k) { if (I.list[k]) cudaFree(I.list[k]); I.list[k] = nullptr; }
+        if (I.tile_list) { cudaFree(I.tile_list); I.tile_list = nullptr; }
+        if (I.lumsq) { cudaFree(I.lumsq); I.lumsq = nullptr; }
+        for (int k = 0; k < 2; ++k) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.list[k]), n_pixels * sizeof(uint32_t)));
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.tile_list), n_pixels * sizeof(uint32_t)));
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.lumsq), n_pixels * sizeof(float)));
+        I.list_capacity = n_pixels;
+    }
+
+    // partition B: the pixels of this rank's tiles
+    const uint32_t* base_list = nullptr;
+    size_t n_local = n_pixels;
+    if (p.tile_parts > 1) {
+        std::vector<uint32_t> mine;
+        const int ts = std::max(p.tile_size, 1);
+        const int tiles_x = (p.width + ts - 1) / ts;
+        for (int y = 0; y < p.height; ++y)
+            for (int x = 0; x < p.width; ++x)
+                if (((y / ts) * tiles_x + (x / ts)) % p.tile_parts == p.tile_part) mine.push_back(uint32_t(y * p.width + x));
+        n_local = mine.size();
+        if (n_local) CUDA_CHECK(cudaMemcpyAsync(I.tile_list, mine.data(), n_local * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        base_list = I.tile_list;
+    }
+
+    if (!p.accumulate) {
+        CUDA_CHECK(cudaMemsetAsync(accum_dev, 0, n_pixels * 3 * sizeof(float), st));
+        if (count_dev) CUDA_CHECK(cudaMemsetAsync(count_dev, 0, n_pixels * sizeof(uint32_t), st));
+    }
+    if (p.adaptive) CUDA_CHECK(cudaMemsetAsync(I.lumsq, 0, n_pixels * sizeof(float), st));
+
+    RoundParams rp{};
+    rp.cam = cam;
+    rp.width = p.width; rp.height = p.height; rp.max_depth = p.max_depth;
+    rp.seed = p.seed; rp.stream = p.stream;
+    rp.accum = accum_dev;
+    rp.count = p.adaptive ? count_dev : nullptr;
+    rp.lumsq = p.adaptive ? I.lumsq : nullptr;
+
+    const int gen_blocks = I.sm_count * 4, ext_blocks = I.sm_count * 8, shade_blocks = I.sm_count * 8;
+    RenderStats S;
+    cudaEvent_t ev_begin, ev_end;
+    CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
+    // per-launch event pairs for the extend kernel (roofline denominator), drained whenever the pool fills up
+    const size_t kPairs = 2048;
+    if (profile && I.ev.size() < kPairs * 2) {
+        I.ev.resize(kPairs * 2);
+        for (auto& e : I.ev) CUDA_CHECK(cudaEventCreate(&e));
+    }
+    size_t pairs_used = 0;
+    auto drain = [&]() {
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < pairs_used; ++k) {
+            float ms = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[2 * k], I.ev[2 * k + 1]));
+            S.extend_ms += ms;
+        }
+        S.extend_launches += pairs_used;
+        pairs_used = 0;
+    };
+
+    CUDA_CHECK(cudaEventRecord(ev_begin, st));
+    k_init_pool<<<(w.pool + 255) / 256, 256, 0, st>>>(w);
+    S.launches++;
+
+    int cur = 0;
+    auto run_round = [&](long long n_list_fixed, const uint32_t* list, uint32_t first_sample, uint32_t batch) {
+        rp.pixel_list = list;
+        rp.first_sample = first_sample;
+        rp.batch = batch;
+        k_round_begin<<<1, 1, 0, st>>>(w.c, n_list_fixed, batch);
+        S.launches++;
+        int check_every = 4;
+        while (true) {
+            for (int k = 0; k < check_every; ++k) {
+                k_generate<<<gen_blocks, 256, 0, st>>>(w, rp, cur);
+                k_after_generate<<<1, 1, 0, st>>>(w.c, cur);
+                if (profile) {
+                    if (pairs_used == kPairs) drain();
+                    CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used], st));
+                }
+                k_extend<<<ext_blocks, 128, 0, st>>>(w, view_, rp, cur);
+                if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used + 1], st)); pairs_used++; }
+                k_shade<<<shade_blocks, 128, 0, st>>>(w, view_, rp, cur);
+                k_after_shade<<<1, 1, 0, st>>>(w.c, cur);
+                cur ^= 1;
+                S.launches += 5;
+                S.waves++;
+            }
+            CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(cudaGetLastError());
+            const WaveCounters& c = *I.counters_host;
+            if (c.issued >= c.total && c.n_extend[cur] == 0) break;
+            if (check_every < 32) check_every *= 2;
+        }
+    };
+
+    if (!p.adaptive) {
+        run_round((long long)n_local, base_list, uint32_t(p.sample_begin), uint32_t(p.samples_per_pixel));
+        S.samples = (unsigned long long)n_local * (unsigned long long)p.samples_per_pixel;
+    } else {
+        // round 0: every local pixel gets min_spp samples; then only the unconverged ones are re-queued
+        const uint32_t max_spp = uint32_t(p.samples_per_pixel);
+        uint32_t first = uint32_t(p.sample_begin);
+        uint32_t batch = uint32_t(std::min(p.adaptive_min_spp, p.samples_per_pixel));
+        const uint32_t* list = base_list;
+        long long n_fixed = (long long)n_local;
+        int flip = 0;
+        unsigned long long issued_total = 0;
+        while (true) {
+            run_round(n_fixed, list, first, batch);
+            issued_total += I.counters_host->total;
+            first += batch;
+            if (first - uint32_t(p.sample_begin) >= max_spp) break;
+            k_adaptive_update<<<I.sm_count * 4, 256, 0, st>>>(w.c, list, I.list[flip], accum_dev, count_dev, I.lumsq,
+                                                              uint32_t(p.adaptive_min_spp), max_spp, float(p.adaptive_threshold));
+            S.launches++;
+            CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            const uint32_t remaining = I.counters_host->n_next_list;
+            if (remaining == 0) break;
+            list = I.list[flip];
+            flip ^= 1;
+            n_fixed = -1;
+            batch = uint32_t(std::min<long long>(p.adaptive_batch_spp, (long long)max_spp - (long long)(first - uint32_t(p.sample_begin))));
+            S.pixels_active = remaining;
+        }
+        S.samples = issued_total;
+        S.pixels_converged = n_local - S.pixels_active;
+    }
+
+    CUDA_CHECK(cudaEventRecord(ev_end, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (profile) drain();
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+    S.elapsed_ms = ms;
+    CUDA_CHECK(cudaMemcpy(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost));
+    S.rays = I.counters_host->rays;
+    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
+    if (stats) *stats = S;
+}
+
+void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
+                           uint32_t* count_out, RenderStats* stats)
+{
+    CUDA_CHECK(cudaSetDevice(device_));
+    const size_t n_pixels = size_t(p.width) * size_t(p.height);
+    std::vector<void*> bag;
+    try {
+        float* d_accum = dev_alloc<float>(bag, n_pixels * 3);
+        uint32_t* d_count = dev_alloc<uint32_t>(bag, n_pixels);
+        uint8_t* d_rgb = dev_alloc<uint8_t>(bag, n_pixels * 3);
+        RenderParams q = p;
+        q.accumulate = 0;
+        render_device(cam, q, d_accum, d_count, stats, false);
+        resolve_device(d_accum, d_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, d_rgb);
+        if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, d_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
+        if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, d_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (count_out) CUDA_CHECK(cudaMemcpy(count_out, d_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    } catch (...) {
+        for (void* q : bag) cudaFree(q);
+        throw;
+    }
+    for (void* q : bag) cudaFree(q);
+}
+
+} // namespace artb

@@ -1,0 +1,88 @@
+// renderer.h — host-callable interface of the CUDA side (implemented in kernels.cu, compiled by nvcc).
+// Everything above it (C-ABI, scene builders, flattener) is plain C++ compiled by g++.
+#ifndef ARTB_RENDERER_H
+#define ARTB_RENDERER_H
+
+#include "flat_scene.h"
+#include "../host/flatten.h"
+
+#include <cstdint>
+#include <string>
+
+namespace artb {
+
+struct RenderParams {
+    int width = 0, height = 0;
+    int samples_per_pixel = 1;
+    int max_depth = 50;
+    uint32_t seed = 1;
+    uint32_t stream = 0;              // Philox key word 1: one stream per rank
+    // partition A (sample split): this call renders per-pixel sample indices [sample_begin, sample_begin+spp)
+    int sample_begin = 0;
+    // partition B (tile split): only tiles with ((ty*tiles_x+tx) % tile_parts) == tile_part are rendered
+    int tile_size = 32, tile_parts = 1, tile_part = 0;
+    // adaptive per-pixel variance mask (0 = off): after min_spp samples a pixel stops once the standard
+    // error of its luminance mean drops below rel_threshold * (mean + 0.05)
+    int adaptive = 0;
+    int adaptive_min_spp = 16;
+    int adaptive_batch_spp = 8;
+    double adaptive_threshold = 0.02;
+    int accumulate = 0;               // 0: accum/count buffers are zeroed first
+};
+
+struct RenderStats {
+    double elapsed_ms = 0;            // CUDA-event time of the whole render (the reference's run() return value)
+    unsigned long long samples = 0;   // primary paths traced
+    unsigned long long rays = 0;      // closest-hit queries (engine.h:455)
+    unsigned long long waves = 0;
+    unsigned long long launches = 0;  // kernels launched
+    double extend_ms = 0, shade_ms = 0, generate_ms = 0, other_ms = 0;   // filled when profile=1
+    unsigned long long extend_launches = 0;
+    unsigned long long pixels_active = 0, pixels_converged = 0;
+};
+
+class Renderer {
+public:
+    Renderer(int device, uint32_t pool_paths);
+    ~Renderer();
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+
+    void upload(const FlatScene& scene);
+    bool has_scene() const { return has_scene_; }
+    uint32_t n_media() const { return view_.n_media; }
+    uint64_t scene_bytes() const { return scene_bytes_; }
+
+    // parity hook: closest hit for explicit rays. rays = n*7 doubles (o, d, time), xi = n*n_media or null.
+    void trace_batch(const double* rays_host, uint64_t n, double t_min, double t_max, const double* xi_host,
+                     HitRecordOut* out_host);
+    // same with device-resident buffers; returns the kernel time in ms
+    float trace_batch_device(const double* rays_dev, uint64_t n, double t_min, double t_max, const double* xi_dev,
+                             HitRecordOut* out_dev);
+
+    // Wavefront render into a device accumulation buffer (W*H*3 float sums) + per-pixel sample counts.
+    void render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
+                       RenderStats* stats, bool profile);
+    // write_color (color.h:6-22) over accum/count -> RGB8 (device buffers)
+    void resolve_device(const float* accum_dev, const uint32_t* count_dev, int n_pixels, int fixed_spp, uint8_t* rgb_dev);
+
+    // convenience: host-buffer render (allocates scratch, copies results back)
+    void render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
+                     uint32_t* count_out, RenderStats* stats);
+
+    void* stream() const { return stream_; }
+    int device() const { return device_; }
+
+private:
+    struct Impl;
+    Impl* impl_;
+    int device_;
+    void* stream_ = nullptr;
+    bool has_scene_ = false;
+    SceneView view_{};
+    uint64_t scene_bytes_ = 0;
+};
+
+} // namespace artb
+
+#endif

@@ -1,0 +1,257 @@
+// rt_intersect.cuh — closest-hit query over the flattened scene (the "extend" stage).
+//
+// Replaces, in one iterative short-stack traversal: hittable_list::hit (hittable_list.cpp:5-19),
+// bvh_node::hit + aabb::hit (bvh.cpp:44-52, aabb.h:16-29), box::hit (box.cpp:17-19), translate::hit and
+// rotate_y::hit (hittable.cpp:3-12, 57-85), sphere / moving_sphere / x?_rect / triangle ::hit and
+// constant_medium::hit (constant_medium.h:37-82).
+//
+// Equivalence argument (DESIGN.md "Closest hit"): every reference leaf computes a candidate t that does
+// not depend on t_max and accepts it iff t_min <= t <= t_max (inclusive), and containers only narrow
+// t_max to the best t so far. Hence the reference returns the minimum-t candidate, ties going to the leaf
+// tested last in its depth-first order. Here leaves may be visited in any order: a candidate replaces the
+// current best iff t < best_t or (t == best_t and dfs_id > best_dfs). Primitive formulas are the
+// reference's, evaluated in double in the primitive's object space (transform chains replayed with the
+// reference's arithmetic), so t is the same number up to FMA contraction.
+#ifndef ARTB_RT_INTERSECT_CUH
+#define ARTB_RT_INTERSECT_CUH
+
+#include "flat_scene.h"
+#include "rt_math.cuh"
+
+namespace artb {
+
+#define ARTB_STACK_DEPTH 64
+
+// ---- transform chains ---------------------------------------------------------------------------
+__device__ __forceinline__ void xform_op_in(const FlatXformOp& op, DRay& r)
+{
+    if (op.type == XFORM_TRANSLATE) {
+        // translate::hit — hittable.cpp:4
+        r.o = r.o - mk3(op.a, op.b, op.c);
+    } else {
+        // rotate_y::hit — hittable.cpp:61-65 (a = sin, b = cos)
+        const double ox = op.b * r.o.x - op.a * r.o.z;
+        const double oz = op.a * r.o.x + op.b * r.o.z;
+        const double dx = op.b * r.d.x - op.a * r.d.z;
+        const double dz = op.a * r.d.x + op.b * r.d.z;
+        r.o.x = ox; r.o.z = oz; r.d.x = dx; r.d.z = dz;
+    }
+}
+
+__device__ __forceinline__ DRay to_object_space(const SceneView& s, uint32_t xform, const DRay& world)
+{
+    DRay r = world;
+    if (xform) {
+        const FlatXform xf = s.xforms[xform];
+        for (uint32_t i = 0; i < xf.n_ops; ++i) xform_op_in(s.xform_ops[xf.first_op + i], r);
+    }
+    return r;
+}
+
+// ---- primitive candidates: t only -----------------------------------------------------------------
+__device__ __forceinline__ bool sphere_t(d3 center, double radius, const DRay& r, double t_min, double t_max, double& t)
+{
+    // sphere.h:40-57
+    const d3 oc = r.o - center;
+    const double a = length_squared(r.d);
+    const double half_b = dot(oc, r.d);
+    const double c = length_squared(oc) - radius * radius;
+    const double discriminant = half_b * half_b - a * c;
+    if (discriminant < 0) return false;
+    const double sqrtd = sqrt(discriminant);
+    double root = (-half_b - sqrtd) / a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < t_min || t_max < root) return false;
+    }
+    t = root;
+    return true;
+}
+
+__device__ __forceinline__ d3 msphere_center(const FlatPrim& p, double time)
+{
+    // moving_sphere.h:29-31
+    const d3 c0 = ld3(p.g), c1 = ld3(p.g + 3);
+    return c0 + ((time - p.g[6]) / (p.g[7] - p.g[6])) * (c1 - c0);
+}
+
+__device__ __forceinline__ bool rect_t(uint32_t type, const double* g, const DRay& r, double t_min, double t_max, double& t)
+{
+    // aarect.cpp:3-55; g = a0 a1 b0 b1 k
+    double ok, dk, oa, da, ob, db;
+    if (type == PRIM_RECT_XY)      { ok = r.o.z; dk = r.d.z; oa = r.o.x; da = r.d.x; ob = r.o.y; db = r.d.y; }
+    else if (type == PRIM_RECT_XZ) { ok = r.o.y; dk = r.d.y; oa = r.o.x; da = r.d.x; ob = r.o.z; db = r.d.z; }
+    else                           { ok = r.o.x; dk = r.d.x; oa = r.o.y; da = r.d.y; ob = r.o.z; db = r.d.z; }
+    const double tt = (g[4] - ok) / dk;
+    if (tt < t_min || tt > t_max) return false;
+    const double a = oa + tt * da;
+    const double b = ob + tt * db;
+    if (a < g[0] || a > g[1] || b < g[2] || b > g[3]) return false;
+    t = tt;
+    return true;
+}
+
+__device__ __forceinline__ bool triangle_t(const double* g, const DRay& r, double t_min, double t_max, double& t)
+{
+    // triangle.h:28-76
+    const d3 pt1 = ld3(g), pt2 = ld3(g + 3), pt3 = ld3(g + 6);
+    const d3 n = cross(pt2 - pt1, pt3 - pt1);
+    const double ndotd = dot(n, r.d);
+    if (fabs(ndotd) < DBL_EPSILON) return false;
+    const double d = -dot(n, pt1);
+    const double tt = -(dot(n, r.o) + d) / ndotd;
+    if (tt < t_min || t_max < tt) return false;
+    const d3 p = r.o + tt * r.d;
+    if (dot(n, cross(pt2 - pt1, p - pt1)) < 0) return false;
+    if (dot(n, cross(pt3 - pt2, p - pt2)) < 0) return false;
+    if (dot(n, cross(pt1 - pt3, p - pt3)) < 0) return false;
+    t = tt;
+    return true;
+}
+
+__device__ __forceinline__ bool surface_t(const FlatPrim& p, const DRay& r, double t_min, double t_max, double& t)
+{
+    switch (p.type) {
+        case PRIM_SPHERE:   return sphere_t(ld3(p.g), p.g[3], r, t_min, t_max, t);
+        case PRIM_MSPHERE:  return sphere_t(msphere_center(p, r.tm), p.g[8], r, t_min, t_max, t);
+        case PRIM_TRIANGLE: return triangle_t(p.g, r, t_min, t_max, t);
+        default:            return rect_t(p.type, p.g, r, t_min, t_max, t);
+    }
+}
+
+// closest boundary hit of a medium: hittable::hit of the boundary sub-graph, scanned like a list
+__device__ inline bool boundary_t(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                                  double t_min, double t_max, double& t)
+{
+    bool any = false;
+    double closest = t_max;
+    uint32_t cached = 0xffffffffu;
+    DRay r = world;
+    for (uint32_t i = first; i < first + count; ++i) {
+        const FlatPrim& p = s.prims[i];
+        if (p.xform != cached) { r = to_object_space(s, p.xform, world); cached = p.xform; }
+        double tt;
+        if (surface_t(p, r, t_min, closest, tt)) { any = true; closest = tt; }
+    }
+    t = closest;
+    return any;
+}
+
+// Source of the one random number a constant_medium consumes per query (constant_medium.h:63):
+// an explicit table (parity hook of artb_trace_batch) or a Philox stream keyed by (path, bounce, medium).
+struct MediumXi {
+    const double* row;       // n_media values for this ray, or nullptr
+    uint32_t seed, stream, path_lo, path_hi, bounce;
+    __device__ __forceinline__ double get(uint32_t slot) const
+    {
+        if (row) return row[slot];
+        Philox g;
+        g.init(seed, stream, path_lo, path_hi, (bounce << 8) | slot, 0x6d656469u /* 'medi' */);
+        return g.next_double();
+    }
+};
+
+__device__ inline bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
+                                const MediumXi& xi, double& t)
+{
+    // constant_medium.h:44-69
+    const uint32_t first = uint32_t(p.g[1]), count = uint32_t(p.g[2]);
+    double t1, t2;
+    if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, t1)) return false;
+    if (!boundary_t(s, first, count, world, t1 + 0.0001, INFINITY, t2)) return false;
+    if (t1 < t_min) t1 = t_min;
+    if (t2 > t_max) t2 = t_max;
+    if (t1 >= t2) return false;
+    if (t1 < 0) t1 = 0;
+    const double ray_length = length(world.d);
+    const double distance_inside_boundary = (t2 - t1) * ray_length;
+    const double u = xi.get(uint32_t(p.g[3]));
+    // explicit-xi table: NaN marks "the reference drew nothing here", i.e. its interval was already empty
+    // because a closer surface had been found first — then this medium cannot be the closest hit either
+    if (!(u == u)) return false;
+    const double hit_distance = p.g[0] * log(u);
+    if (hit_distance > distance_inside_boundary) return false;
+    t = t1 + hit_distance / ray_length;
+    return true;
+}
+
+// ---- BVH traversal ------------------------------------------------------------------------------
+struct ClosestHit { double t; int32_t prim; uint32_t dfs; };
+
+__device__ __forceinline__ void test_leaf(const SceneView& s, int32_t first, int32_t count, const DRay& world,
+                                          double t_min, const MediumXi& xi, ClosestHit& best,
+                                          uint32_t& cached_xform, DRay& cached_ray)
+{
+    for (int32_t i = first; i < first + count; ++i) {
+        const FlatPrim& p = s.prims[i];
+        double t;
+        bool ok;
+        if (p.type == PRIM_MEDIUM) {
+            ok = medium_t(s, p, world, t_min, best.t, xi, t);
+        } else {
+            if (p.xform != cached_xform) { cached_ray = to_object_space(s, p.xform, world); cached_xform = p.xform; }
+            ok = surface_t(p, cached_ray, t_min, best.t, t);
+        }
+        if (ok && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
+            best.t = t; best.prim = i; best.dfs = p.dfs_id;
+        }
+    }
+}
+
+// slab test against [t_min, t_best]; NaNs (0 * inf) are ignored by fmin/fmax exactly as the reference's
+// comparisons ignore them (aabb.h:22-23). Inclusive, so equal-t candidates are still visited.
+__device__ __forceinline__ bool slab(const double* lo, const double* hi, d3 o, d3 inv, double t_min, double t_best, double& enter)
+{
+    const double x0 = (lo[0] - o.x) * inv.x, x1 = (hi[0] - o.x) * inv.x;
+    const double y0 = (lo[1] - o.y) * inv.y, y1 = (hi[1] - o.y) * inv.y;
+    const double z0 = (lo[2] - o.z) * inv.z, z1 = (hi[2] - o.z) * inv.z;
+    const double tn = fmax(fmax(fmin(x0, x1), fmin(y0, y1)), fmax(fmin(z0, z1), t_min));
+    const double tf = fmin(fmin(fmax(x0, x1), fmax(y0, y1)), fmin(fmax(z0, z1), t_best));
+    enter = tn;
+    return tn <= tf;
+}
+
+__device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi)
+{
+    ClosestHit best;
+    best.t = t_max; best.prim = -1; best.dfs = 0;
+    uint32_t cached_xform = 0;
+    DRay cached_ray = ray;
+
+    if (s.root_count > 0) {
+        test_leaf(s, s.root_child, s.root_count, ray, t_min, xi, best, cached_xform, cached_ray);
+        return best;
+    }
+    if (s.n_world_prims == 0) return best;
+
+    const d3 inv = mk3(1.0 / ray.d.x, 1.0 / ray.d.y, 1.0 / ray.d.z);
+    int32_t stack[ARTB_STACK_DEPTH];
+    int sp = 0;
+    int32_t node = s.root_child;
+    while (true) {
+        const FlatNode& n = s.nodes[node];
+        double e0, e1;
+        const bool h0 = slab(n.lo0, n.hi0, ray.o, inv, t_min, best.t, e0);
+        const bool h1 = slab(n.lo1, n.hi1, ray.o, inv, t_min, best.t, e1);
+        int32_t next = -1;
+        if (h0 && n.count0 > 0) test_leaf(s, n.child0, n.count0, ray, t_min, xi, best, cached_xform, cached_ray);
+        if (h1 && n.count1 > 0) test_leaf(s, n.child1, n.count1, ray, t_min, xi, best, cached_xform, cached_ray);
+        const bool i0 = h0 && n.count0 == 0, i1 = h1 && n.count1 == 0;
+        if (i0 && i1) {
+            const bool first0 = e0 <= e1;
+            next = first0 ? n.child0 : n.child1;
+            if (sp < ARTB_STACK_DEPTH) stack[sp++] = first0 ? n.child1 : n.child0;
+        } else if (i0) next = n.child0;
+        else if (i1) next = n.child1;
+        if (next < 0) {
+            if (sp == 0) break;
+            next = stack[--sp];
+        }
+        node = next;
+    }
+    return best;
+}
+
+} // namespace artb
+
+#endif

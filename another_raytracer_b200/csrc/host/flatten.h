@@ -1,0 +1,59 @@
+// Host-side BVH flattener: pointer-based scene graph -> linear arrays for the device (flat_scene.h).
+//
+// What it preserves from the reference, so that closest-hit results stay bit-compatible:
+//  * dfs_id — the order in which the reference's recursive traversal (hittable_list.cpp:5-19 in insertion
+//    order, bvh.cpp:44-52 left then right, box.cpp:17-19 six sides, wrappers hittable.cpp:3-12/57-85) tests
+//    the leaves. Every reference leaf accepts t == t_max, so among equal-t candidates the one tested LAST
+//    wins; the device applies "larger dfs_id wins ties" under its own traversal order.
+//  * culling — a reference bvh_node whose box has zero thickness on some axis can never be entered
+//    (aabb.h:25 rejects t_max <= t_min), so every leaf below it is unreachable; such leaves keep their
+//    dfs_id but are dropped from the device arrays.
+//  * transform chains — translate / rotate_y wrappers are recorded per primitive (outermost first) and
+//    replayed on the device with the reference's exact arithmetic, including the face-normal re-orientation
+//    each wrapper performs on the way out.
+//  * media — constant_medium becomes one primitive whose boundary sub-graph is flattened into a private
+//    primitive range (scanned linearly, in dfs order, exactly like a hittable_list).
+// What it replaces: the reference's trees. One binned-SAH binary BVH is built over the WORLD-space boxes
+// of all reachable world primitives.
+#ifndef ARTB_HOST_FLATTEN_H
+#define ARTB_HOST_FLATTEN_H
+
+#include "scene.h"
+#include "../device/flat_scene.h"
+
+#include <vector>
+
+namespace artb {
+
+struct FlatScene {
+    std::vector<FlatPrim> prims;          // [0, n_world_prims) in BVH leaf order, then boundary prims
+    std::vector<FlatNode> nodes;
+    std::vector<FlatXformOp> xform_ops;
+    std::vector<FlatXform> xforms;        // [0] = identity
+    std::vector<FlatMaterial> materials;
+    std::vector<FlatTexture> textures;
+    std::vector<FlatImage> images;
+    std::vector<unsigned char> texels;
+    std::vector<FlatPerlin> perlins;
+    uint32_t n_world_prims = 0;
+    uint32_t n_media = 0;
+    uint32_t n_leaves_total = 0;          // dfs ids handed out (reachable or not)
+    uint32_t n_culled = 0;
+    int32_t root_child = 0, root_count = 0;
+    double background[3] = {0, 0, 0};
+    double world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
+    int bvh_depth = 0;
+};
+
+struct FlattenOptions {
+    int max_leaf_prims = 4;
+    int sah_bins = 16;
+    double traversal_cost = 1.0;
+    double intersect_cost = 1.5;
+};
+
+FlatScene flatten(const hittable_list& world, const color& background, const FlattenOptions& opt = FlattenOptions());
+
+} // namespace artb
+
+#endif

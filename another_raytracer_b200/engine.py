@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's render seam on top of the C ABI.
+
+Reference: `engine<W,H,C>{set_scene, run}` + `engine_mode` (src/engine/engine.h:10-54), `scene_manager::build`
+(src/scene_manager.h:29-44), `camera` (src/engine/camera.h:8-17). Same names, argument meaning and error behaviour:
+`Engine.run` returns the elapsed milliseconds, or -1 after printing "Invalid input scene!" when no scene is set.
+All work is done by libartb.so on the GPU; numpy/torch only carry buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import sys
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi
+
+HIT_DTYPE = np.dtype([("t", "<f8"), ("p", "<f8", 3), ("normal", "<f8", 3), ("u", "<f8"), ("v", "<f8"),
+                      ("hit", "<i4"), ("prim_id", "<i4"), ("front_face", "<i4"), ("material_type", "<i4")])
+assert HIT_DTYPE.itemsize == C.sizeof(_abi.Hit)
+
+MATERIAL_NAMES = ["lambertian", "metal", "dielectric", "diffuse_light", "isotropic"]
+
+
+class ArtbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"artb error {code}: {message}")
+        self.code = code
+
+
+class SceneAlias(enum.IntEnum):
+    """scene_alias of the reference (scene_manager.h:16-27) + the added mesh / synthetic scenes."""
+    random = 1
+    two_spheres = 2
+    two_perlin_spheres = 3
+    earth = 4
+    simple_light = 5
+    cornell_box = 6
+    cornell_smoke = 7
+    final = 8
+    mesh = 9
+    cow = 10
+    dino = 11
+    heightfield = 12
+
+
+class EngineMode(enum.Enum):
+    """engine_mode of the reference (engine.h:10-16). On the GPU `single`, `parallel_stripes` and
+    `parallel_images` are the same fixed-spp wavefront render; `adaptive` selects the per-pixel variance mask."""
+    single = 0
+    adaptive = 1
+    parallel_stripes = 2
+    parallel_images = 3
+
+
+def _check(rc: int, ctx=None):
+    if rc != 0:
+        msg = _abi.load().artb_last_error(ctx)
+        raise ArtbError(rc, (msg or b"").decode(errors="replace"))
+
+
+class Scene:
+    """A host scene graph built by the C++ scene_manager mirror, plus its flattened arrays."""
+
+    def __init__(self, handle):
+        self._h = handle
+        info = _abi.SceneInfo()
+        _check(_abi.load().artb_scene_get_info(self._h, C.byref(info)))
+        self.info = {name: (list(getattr(info, name)) if hasattr(getattr(info, name), "__len__") else getattr(info, name))
+                     for name, _ in _abi.SceneInfo._fields_}
+
+    @classmethod
+    def build(cls, alias, mesh_as_soup: bool = False, heightfield_side: int = 0, max_leaf_prims: int = 0,
+              assets_root: str | None = None) -> "Scene":
+        lib = _abi.load()
+        opt = _abi.SceneOptions(int(mesh_as_soup), int(heightfield_side), int(max_leaf_prims), 0,
+                                assets_root.encode() if assets_root else None)
+        h = C.c_void_p()
+        _check(lib.artb_scene_build(int(alias), C.byref(opt), C.byref(h)))
+        return cls(h)
+
+    def dump_graph(self) -> np.ndarray:
+        lib = _abi.load()
+        n = lib.artb_scene_dump_graph(self._h, None, 0)
+        if n < 0:
+            _check(int(n))
+        out = np.empty(n, dtype=np.float64)
+        lib.artb_scene_dump_graph(self._h, out.ctypes.data, n)
+        return out
+
+    def flat_view(self) -> _abi.FlatSceneView:
+        v = _abi.FlatSceneView()
+        _check(_abi.load().artb_scene_get_flat(self._h, C.byref(v)))
+        return v
+
+    def camera(self, width: int, height: int) -> "CameraDesc":
+        """The camera src/main.cpp:33-35 builds for this scene: vup (0,1,0), focus 10, shutter [0,1)."""
+        i = self.info
+        return CameraDesc(i["lookfrom"], i["lookat"], (0.0, 1.0, 0.0), i["vfov"], width / height, i["aperture"], 10.0, 0.0, 1.0)
+
+    def close(self):
+        if self._h:
+            _abi.load().artb_scene_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class CameraDesc:
+    """Arguments of camera::camera (camera.h:8-17)."""
+    lookfrom: tuple
+    lookat: tuple
+    vup: tuple = (0.0, 1.0, 0.0)
+    vfov: float = 40.0
+    aspect_ratio: float = 1.0
+    aperture: float = 0.0
+    focus_dist: float = 10.0
+    time0: float = 0.0
+    time1: float = 0.0
+
+    def to_c(self) -> _abi.Camera:
+        d3 = C.c_double * 3
+        return _abi.Camera(d3(*self.lookfrom), d3(*self.lookat), d3(*self.vup), self.vfov, self.aspect_ratio,
+                           self.aperture, self.focus_dist, self.time0, self.time1)
+
+
+@dataclass
+class RenderOptions:
+    width: int
+    height: int
+    samples_per_pixel: int
+    max_depth: int = 50
+    seed: int = 1
+    stream: int = 0
+    mode: int = _abi.MODE_FIXED
+    sample_begin: int = 0
+    tile_size: int = 32
+    tile_parts: int = 1
+    tile_part: int = 0
+    adaptive_min_spp: int = 16
+    adaptive_batch_spp: int = 8
+    adaptive_threshold: float = 0.02
+    accumulate: bool = False
+    profile: bool = False
+
+    def to_c(self) -> _abi.RenderParams:
+        return _abi.RenderParams(self.width, self.height, self.samples_per_pixel, self.max_depth, self.seed, self.stream,
+                                 self.mode, self.sample_begin, self.tile_size, self.tile_parts, self.tile_part,
+                                 self.adaptive_min_spp, self.adaptive_batch_spp, self.adaptive_threshold,
+                                 int(self.accumulate), int(self.profile))
+
+
+def _stats_dict(s: _abi.Stats) -> dict:
+    return {name: getattr(s, name) for name, _ in _abi.Stats._fields_}
+
+
+class Context:
+    """One GPU: artb_ctx."""
+
+    def __init__(self, device: int = 0, pool_paths: int = 0):
+        lib = _abi.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        cfg = _abi.Config(device, pool_paths)
+        _check(lib.artb_create(C.byref(cfg), C.byref(self._h)))
+        self.n_media = 0
+
+    def upload(self, scene: Scene):
+        _check(self._lib.artb_upload_scene(self._h, scene._h), self._h)
+        self.n_media = scene.info["n_media"]
+
+    def upload_flat(self, view: _abi.FlatSceneView):
+        _check(self._lib.artb_upload_flat(self._h, C.byref(view)), self._h)
+        self.n_media = view.n_media
+
+    def trace_batch(self, rays: np.ndarray, t_min: float = 0.001, t_max: float = float("inf"),
+                    medium_xi: np.ndarray | None = None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = rays.shape[0]
+        out = np.zeros(n, dtype=HIT_DTYPE)
+        xi_ptr = None
+        if medium_xi is not None and self.n_media:
+            medium_xi = np.ascontiguousarray(medium_xi, dtype=np.float64).reshape(n, self.n_media)
+            xi_ptr = medium_xi.ctypes.data
+        _check(self._lib.artb_trace_batch(self._h, rays.ctypes.data, n, t_min, t_max, xi_ptr, out.ctypes.data), self._h)
+        return out
+
+    def trace_batch_device(self, rays_ptr: int, n: int, hits_ptr: int, t_min: float = 0.001, t_max: float = float("inf"),
+                           xi_ptr: int | None = None) -> float:
+        ms = C.c_float(0)
+        _check(self._lib.artb_trace_batch_device(self._h, rays_ptr, n, t_min, t_max, xi_ptr, hits_ptr, C.byref(ms)), self._h)
+        return ms.value
+
+    def render(self, cam: CameraDesc, opt: RenderOptions, want_accum: bool = False, want_count: bool = False):
+        """artb_render: host buffers in and out. Returns (rgb8[H,W,3], stats, accum|None, count|None)."""
+        rgb = np.zeros((opt.height, opt.width, 3), dtype=np.uint8)
+        accum = np.zeros((opt.height, opt.width, 3), dtype=np.float32) if want_accum else None
+        count = np.zeros((opt.height, opt.width), dtype=np.uint32) if want_count else None
+        st = _abi.Stats()
+        c, p = cam.to_c(), opt.to_c()
+        _check(self._lib.artb_render(self._h, C.byref(c), C.byref(p), rgb.ctypes.data,
+                                     accum.ctypes.data if want_accum else None,
+                                     count.ctypes.data if want_count else None, C.byref(st)), self._h)
+        return rgb, _stats_dict(st), accum, count
+
+    def render_device(self, cam: CameraDesc, opt: RenderOptions, accum_ptr: int, count_ptr: int | None = None) -> dict:
+        st = _abi.Stats()
+        c, p = cam.to_c(), opt.to_c()
+        _check(self._lib.artb_render_device(self._h, C.byref(c), C.byref(p), accum_ptr, count_ptr, C.byref(st)), self._h)
+        return _stats_dict(st)
+
+    def resolve_device(self, accum_ptr: int, count_ptr: int | None, n_pixels: int, fixed_spp: int, rgb_ptr: int):
+        _check(self._lib.artb_resolve_device(self._h, accum_ptr, count_ptr, n_pixels, fixed_spp, rgb_ptr), self._h)
+
+    @property
+    def stream(self) -> int:
+        return self._lib.artb_stream(self._h) or 0
+
+    def close(self):
+        if self._h:
+            self._lib.artb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """engine<W,H,3> of the reference (engine.h:18-54), runtime-sized.
+
+        eng = Engine(cam, EngineMode.single, width=800, height=800, samples_per_pixel=100)
+        eng.set_scene(scene)
+        ms = eng.run(output_image)       # output_image: uint8 array of W*H*3, row 0 = top
+    """
+
+    def __init__(self, cam: CameraDesc, mode: EngineMode = EngineMode.single, *, width: int, height: int,
+                 samples_per_pixel: int = 100, max_depth: int = 50, seed: int = 1, device: int = 0,
+                 context: Context | None = None):
+        self.cam = cam
+        self.mode = mode
+        self.width, self.height = width, height
+        self.samples_per_pixel, self.max_depth, self.seed = samples_per_pixel, max_depth, seed
+        self._ctx = context
+        self._device = device
+        self._scene = None
+        self.last_stats: dict = {}
+
+    def set_scene(self, scene: Scene | None):
+        self._scene = scene
+        if scene is not None and scene.info["top_level_objects"] > 0:
+            if self._ctx is None:
+                self._ctx = Context(self._device)
+            self._ctx.upload(scene)
+
+    def run(self, output_image: np.ndarray) -> int:
+        if self._scene is None or self._scene.info["top_level_objects"] == 0 or self._ctx is None:
+            print("Invalid input scene!", file=sys.stderr)      # engine.h:32-36
+            return -1
+        if self.mode is EngineMode.adaptive and (self.width % 12 or self.height % 12):
+            # engine.h:182-183 — kept so that callers relying on the reference's contract see the same failure
+            raise ValueError("for adaptive strategy image size should perfectly fit big square size for now!!")
+        opt = RenderOptions(self.width, self.height, self.samples_per_pixel, self.max_depth, self.seed,
+                            mode=_abi.MODE_VARIANCE_MASK if self.mode is EngineMode.adaptive else _abi.MODE_FIXED)
+        rgb, stats, _, _ = self._ctx.render(self.cam, opt)
+        np.copyto(np.asarray(output_image).reshape(self.height, self.width, 3), rgb)
+        self.last_stats = stats
+        return int(round(stats["elapsed_ms"]))

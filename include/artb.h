@@ -1,0 +1,180 @@
+/* artb.h — C ABI of the B200 path-tracing backend for blackccpie/another_raytracer.
+ *
+ * The reference has no plugin / FFI interface; the seam this library sits behind is the three-method
+ * contract of its render driver (reference: src/engine/engine.h:18-54, used by src/main.cpp:44-46):
+ *
+ *     engine<W,H,C> eng(cam, mode);  eng.set_scene(world.objects, world.background);  ms = eng.run(out);
+ *
+ * Each entry point below cites the reference interface it replaces. Conventions: plain pointers and sizes
+ * only; every function returns 0 on success or a negative artb_status and never throws across the ABI;
+ * artb_last_error() gives the message; buffers are caller-owned; calls are blocking; one context per host
+ * thread. There is NO CPU fallback: artb_create fails with ARTB_E_NO_DEVICE when no CUDA device exists.
+ */
+#ifndef ARTB_H
+#define ARTB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "artb_tokens.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARTB_ABI_VERSION 1
+
+typedef enum artb_status {
+    ARTB_OK = 0,
+    ARTB_E_INVALID = -1,       /* bad argument */
+    ARTB_E_NO_DEVICE = -2,     /* no CUDA device / CUDA runtime failure at start-up */
+    ARTB_E_CUDA = -3,          /* CUDA error while running */
+    ARTB_E_SCENE = -4,         /* scene cannot be built / flattened (unsupported graph, missing asset) */
+    ARTB_E_EMPTY_SCENE = -5,   /* reference: engine::run returns -1 and prints "Invalid input scene!" (engine.h:32-36) */
+    ARTB_E_ADAPTIVE_SIZE = -6  /* reference: std::logic_error when W or H is not a multiple of 12 (engine.h:182-183) */
+} artb_status;
+
+typedef struct artb_ctx artb_ctx;       /* one GPU + its path pool               */
+typedef struct artb_scene artb_scene;   /* host scene graph + its flattened form */
+
+/* ---- context ------------------------------------------------------------------------------------ */
+typedef struct artb_config {
+    int32_t device;            /* CUDA device ordinal */
+    uint32_t pool_paths;       /* paths in flight (0 = default 2 Mi) */
+} artb_config;
+
+int artb_abi_version(void);
+int artb_create(const artb_config* cfg, artb_ctx** out);
+void artb_destroy(artb_ctx* ctx);
+/* message of the last failing call on this context (ctx may be NULL: last failure of a ctx-less call) */
+const char* artb_last_error(const artb_ctx* ctx);
+
+/* ---- host scene construction (replaces scene_manager::build, src/scene_manager.cpp:260-355) ----- */
+typedef struct artb_scene_options {
+    int32_t mesh_as_soup;      /* aliases 9-11: flatten the .obj as one triangle_soup (no per-triangle objects) */
+    int32_t heightfield_side;  /* alias 12: vertices per side (0 = 708 -> 999 698 triangles) */
+    int32_t max_leaf_prims;    /* device BVH leaf size (0 = default) */
+    int32_t reserved;
+    const char* assets_root;   /* NULL: $ARTB_ASSETS or <repo>/assets */
+} artb_scene_options;
+
+typedef struct artb_scene_info {
+    double lookfrom[3], lookat[3], vfov, aperture, background[3];   /* scene_manager.h:6-14 */
+    double rng_next;           /* next value of the global RNG after the build (pins RNG consumption) */
+    double world_lo[3], world_hi[3];
+    uint64_t rng_draws;
+    uint32_t n_prims, n_world_prims, n_nodes, n_media, n_materials, n_textures, n_images, n_xforms;
+    uint32_t n_leaves_total, n_culled, bvh_depth, top_level_objects;
+    uint64_t flat_bytes;
+} artb_scene_info;
+
+/* alias: 1..9 = the reference's scene_alias (scene_manager.h:16-27); 10 cow, 11 dino, 12 height field.
+ * The global host RNG is reset to its default seed first, so every build sees the stream a fresh
+ * reference process would. */
+int artb_scene_build(int32_t alias, const artb_scene_options* opt, artb_scene** out);
+void artb_scene_free(artb_scene* s);
+int artb_scene_get_info(const artb_scene* s, artb_scene_info* out);
+/* pre-order token stream of the host graph (artb_tokens.h). Returns the stream length; copies at most
+ * `capacity` doubles into out (out may be NULL to query the length). */
+int64_t artb_scene_dump_graph(const artb_scene* s, double* out, int64_t capacity);
+
+/* ---- flattened scene as plain arrays (what a foreign host hands over) ----------------- */
+typedef struct artb_flat_scene {
+    const void* prims;      uint32_t n_prims, n_world_prims;   /* FlatPrim[],   96 B each  */
+    const void* nodes;      uint32_t n_nodes; int32_t root_child, root_count, bvh_depth;   /* FlatNode[], 128 B */
+    const void* xform_ops;  uint32_t n_xform_ops;              /* FlatXformOp[], 32 B      */
+    const void* xforms;     uint32_t n_xforms;                 /* FlatXform[],    8 B      */
+    const void* materials;  uint32_t n_materials;              /* FlatMaterial[], 48 B     */
+    const void* textures;   uint32_t n_textures;               /* FlatTexture[],  96 B     */
+    const void* images;     uint32_t n_images;                 /* FlatImage[],    24 B     */
+    const unsigned char* texels; uint64_t n_texel_bytes;
+    const void* perlins;    uint32_t n_perlins;                /* FlatPerlin[], 9216 B     */
+    uint32_t n_media;
+    double background[3];
+} artb_flat_scene;
+
+/* view of the arrays owned by `s` (valid until artb_scene_free) */
+int artb_scene_get_flat(const artb_scene* s, artb_flat_scene* out);
+
+/* ---- engine::set_scene (engine.h:24-28): copy the scene to HBM ------------------------------------ */
+int artb_upload_scene(artb_ctx* ctx, const artb_scene* s);
+int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* flat);
+
+/* ---- parity hook: hittable_list::hit on explicit rays (engine.h:455, hittable_list.cpp:5-19) ----- */
+typedef struct artb_hit {
+    double t, p[3], normal[3], u, v;     /* hit_record, hittable.h:9-16 */
+    int32_t hit;                         /* 0 = miss */
+    int32_t prim_id;                     /* leaf id in the reference's depth-first order, -1 on miss */
+    int32_t front_face;
+    int32_t material_type;               /* 0 lambertian 1 metal 2 dielectric 3 diffuse_light 4 isotropic */
+} artb_hit;
+
+/* rays: n x 7 doubles (origin, direction, time); medium_xi: n x n_media doubles, the random number each
+ * constant_medium consumes for that ray (constant_medium.h:63), NaN where the reference drew none;
+ * NULL = draw from the Philox stream. All pointers are HOST pointers. */
+int artb_trace_batch(artb_ctx* ctx, const double* rays, uint64_t n, double t_min, double t_max,
+                     const double* medium_xi, artb_hit* hits_out);
+/* same on DEVICE pointers; *kernel_ms (optional) receives the CUDA-event time of the traversal kernel */
+int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, double t_min, double t_max,
+                            const double* medium_xi_dev, artb_hit* hits_dev, float* kernel_ms);
+
+/* ---- engine::run (engine.h:30-54) ------------------------------------------------------------------ */
+typedef struct artb_camera {            /* camera::camera arguments, camera.h:8-17 */
+    double lookfrom[3], lookat[3], vup[3];
+    double vfov, aspect_ratio, aperture, focus_dist, time0, time1;
+} artb_camera;
+
+typedef enum artb_mode {
+    ARTB_MODE_FIXED = 0,                /* engine_mode::single / parallel_*: spp samples for every pixel */
+    ARTB_MODE_VARIANCE_MASK = 1         /* north_star (3): per-pixel variance mask, unconverged pixels re-queued */
+} artb_mode;
+
+typedef struct artb_render_params {
+    int32_t width, height;              /* engine<W,H,3> template arguments */
+    int32_t samples_per_pixel;          /* tracer_constants::samples_per_pixel; cap in variance-mask mode */
+    int32_t max_depth;                  /* tracer_constants::max_depth (0 = 50) */
+    uint32_t seed;
+    uint32_t stream;                    /* Philox stream: use the rank for sample-split rendering */
+    int32_t mode;                       /* artb_mode */
+    int32_t sample_begin;               /* partition A: first per-pixel sample index of this call */
+    int32_t tile_size, tile_parts, tile_part;   /* partition B: interleaved tiles (tile_parts<=1: whole image) */
+    int32_t adaptive_min_spp, adaptive_batch_spp;
+    double adaptive_threshold;          /* relative standard error of the pixel luminance mean */
+    int32_t accumulate;                 /* device variant: add to the buffers instead of clearing them */
+    int32_t profile;                    /* time every extend launch with CUDA events (stats.extend_ms) */
+} artb_render_params;
+
+typedef struct artb_stats {
+    double elapsed_ms;                  /* what engine::run returns (engine.h:91-93), measured with CUDA events */
+    uint64_t samples, rays, waves, launches;
+    double extend_ms; uint64_t extend_launches;
+    uint64_t pixels_active, pixels_converged;
+    uint64_t h2d_bytes, d2h_bytes;
+} artb_stats;
+
+/* rgb8_out: W*H*3 bytes, row 0 = top, RGB (the layout engine::run writes). accum_out (optional):
+ * W*H*3 float per-pixel radiance SUMS; count_out (optional): W*H samples per pixel. HOST pointers. */
+int artb_render(artb_ctx* ctx, const artb_camera* cam, const artb_render_params* p, uint8_t* rgb8_out,
+                float* accum_out, uint32_t* count_out, artb_stats* stats);
+/* DEVICE pointers; no resolve. For multi-GPU: every rank renders its share, the sums are reduced, rank 0
+ * resolves. count_dev may be NULL in ARTB_MODE_FIXED. */
+int artb_render_device(artb_ctx* ctx, const artb_camera* cam, const artb_render_params* p, float* accum_dev,
+                       uint32_t* count_dev, artb_stats* stats);
+/* write_color (color.h:6-22) on DEVICE buffers: fixed_spp > 0 divides by it, else by count_dev */
+int artb_resolve_device(artb_ctx* ctx, const float* accum_dev, const uint32_t* count_dev, int32_t n_pixels,
+                        int32_t fixed_spp, uint8_t* rgb8_dev);
+/* the CUDA stream the context launches on (cudaStream_t) */
+void* artb_stream(artb_ctx* ctx);
+
+/* ---- imageio::save_image / load_image (imageio.h:9-10) --------------------------------------------- */
+int artb_save_png(const char* path, int32_t width, int32_t height, int32_t channels, const uint8_t* data);
+
+/* ---- host RNG (tracer_utils.h:27-41), exposed so tests can pin it -------------------------------- */
+void artb_host_rng_reset(uint32_t seed);
+double artb_host_rng_next(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

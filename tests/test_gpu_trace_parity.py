@@ -1,0 +1,145 @@
+"""GPU parity, first gate (north_star): on fixed ray batches the BVH traversal must return the same hit primitive id
+as the reference (bit-exact) with t / normal within 1e-5 relative.
+
+Fixtures: tests/golden/trace_<alias>.npz — every closest-hit query the UNMODIFIED reference made while path tracing a
+sparse pixel grid of each scene (primary rays and all bounces, rays inside glass, rays through media), with the winning
+leaf's depth-first id and the random number each constant_medium consumed (tools/make_golden.py). Calls go through the
+C ABI (artb_trace_batch) with host buffers.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5          # north_star tolerance for t and the normal
+ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
+MAT_CODE = {200: 0, 201: 1, 202: 2, 203: 3, 204: 4}
+
+
+@pytest.fixture(scope="module")
+def scenes(artb):
+    cache = {}
+
+    def get(alias):
+        if alias not in cache:
+            cache[alias] = artb.Scene.build(alias)
+        return cache[alias]
+    return get
+
+
+@pytest.mark.parametrize("alias", ALIASES)
+def test_closest_hit_matches_reference(artb, gpu_ctx, scenes, alias):
+    g = np.load(GOLDEN / f"trace_{alias}.npz")
+    scene = scenes(alias)
+    assert scene.info["n_leaves_total"] == int(g["n_leaves"])
+    assert scene.info["n_media"] == int(g["n_media"])
+    gpu_ctx.upload(scene)
+    out = gpu_ctx.trace_batch(g["rays"], 0.001, float("inf"), g["xi"] if int(g["n_media"]) else None)
+
+    ref_hit = g["hit"].astype(bool)
+    assert np.array_equal(out["hit"].astype(bool), ref_hit), "hit / miss decisions differ"
+    h = ref_hit
+    # primitive id: bit-exact
+    bad = np.nonzero(out["prim_id"][h] != g["prim"][h])[0]
+    assert bad.size == 0, f"{bad.size} of {h.sum()} primitive ids differ, first at hit #{bad[:5]}"
+    assert np.all(out["prim_id"][~h] == -1)
+    # t, p, normal: 1e-5 relative
+    t_ref, t_gpu = g["t"][h], out["t"][h]
+    assert np.max(np.abs(t_gpu - t_ref) / np.abs(t_ref)) <= REL_TOL
+    n_ref, n_gpu = g["normal"][h], out["normal"][h]
+    scale = np.maximum(np.linalg.norm(n_ref, axis=1, keepdims=True), 1e-300)
+    assert np.max(np.abs(n_gpu - n_ref) / scale) <= REL_TOL
+    p_ref, p_gpu = g["p"][h], out["p"][h]
+    pscale = np.maximum(np.linalg.norm(p_ref, axis=1, keepdims=True), 1.0)
+    assert np.max(np.abs(p_gpu - p_ref) / pscale) <= REL_TOL
+    # face orientation and material class
+    assert np.array_equal(out["front_face"][h], g["ff"][h])
+    assert np.array_equal(out["material_type"][h], np.vectorize(MAT_CODE.get)(g["mat"][h]))
+    # u,v wherever the reference defines them (moving spheres and media leave them untouched)
+    has_uv = h.copy()
+    has_uv[h] = np.isin(g["mat"][h], [200, 201, 202, 203]) & ~_is_moving_or_medium(scene, g, h)
+    if has_uv.any():
+        assert np.max(np.abs(out["u"][has_uv] - g["uv"][has_uv, 0])) <= 1e-7
+        assert np.max(np.abs(out["v"][has_uv] - g["uv"][has_uv, 1])) <= 1e-7
+
+
+def _is_moving_or_medium(scene, g, h):
+    """leaf ids whose record has no u,v of its own: found from the graph token stream"""
+    stream = scene.dump_graph()
+    no_uv = set(_leaf_ids_without_uv(stream))
+    return np.array([int(i) in no_uv for i in g["prim"][h]])
+
+
+def _leaf_ids_without_uv(s):
+    """walk the pre-order token stream (include/artb_tokens.h) and number leaves like the flattener does"""
+    pos, next_id, out = 0, 0, []
+
+    def tex():
+        nonlocal pos
+        t = int(s[pos]); pos += 1
+        if t == 300: pos += 3
+        elif t == 301: tex(); tex()
+        elif t == 302: pos += 3
+        elif t == 303: pos += 5
+        elif t == 304: pos += 6; tex()
+        elif t == 305: pos += 9
+        else: raise AssertionError(f"texture token {t}")
+
+    def mat():
+        nonlocal pos
+        t = int(s[pos]); pos += 1
+        if t in (200, 203, 204): tex()
+        elif t == 201: pos += 4
+        elif t == 202: pos += 1
+        else: raise AssertionError(f"material token {t}")
+
+    def node():
+        nonlocal pos, next_id
+        t = int(s[pos]); pos += 1
+        if t == 100:
+            n = int(s[pos]); pos += 1
+            for _ in range(n): node()
+        elif t == 101:
+            same = int(s[pos + 6]); pos += 7
+            node()
+            if not same: node()
+        elif t == 102: pos += 3; node()
+        elif t == 103: pos += 9; node()
+        elif t == 104: pos += 6; node()
+        elif t == 110: pos += 4; mat(); next_id += 1
+        elif t == 111: pos += 9; mat(); out.append(next_id); next_id += 1
+        elif t in (112, 113, 114): pos += 5; mat(); next_id += 1
+        elif t == 115: pos += 9; mat(); next_id += 1
+        elif t == 116:
+            pos += 1; mat(); out.append(next_id); next_id += 1; node()
+        else: raise AssertionError(f"hittable token {t}")
+
+    node()
+    assert pos == len(s)
+    return out
+
+
+def test_tmax_and_tmin_window(artb, gpu_ctx, scenes):
+    """t_min/t_max are honoured inclusively like the reference's `root < t_min || t_max < root` tests."""
+    g = np.load(GOLDEN / "trace_6.npz")
+    gpu_ctx.upload(scenes(6))
+    h = g["hit"].astype(bool)
+    rays, t = g["rays"][h][:512], g["t"][h][:512]
+    # a window ending exactly at the hit still reports it; one ending just before reports something else or a miss
+    for i in range(0, 512, 37):
+        a = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, float(t[i]))
+        assert a["hit"][0] == 1 and a["t"][0] == pytest.approx(t[i], rel=1e-12)
+        b = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, float(np.nextafter(t[i], 0) * (1 - 1e-9)))
+        assert b["hit"][0] == 0 or b["t"][0] < t[i]
+
+
+def test_empty_batch_and_no_scene(artb):
+    ctx = artb.Context(0, 1 << 12)
+    with pytest.raises(artb.ArtbError) as e:
+        ctx.trace_batch(np.zeros((1, 7)))
+    assert e.value.code == -5 and "Invalid input scene" in str(e.value)
+    ctx.upload(artb.Scene.build(2))
+    assert ctx.trace_batch(np.zeros((0, 7))).shape == (0,)
+    ctx.close()
