@@ -3,6 +3,7 @@
 #include "artb_tokens.h"
 
 #include <stdexcept>
+#include <unordered_map>
 
 namespace artb {
 
@@ -22,10 +23,15 @@ struct writer {
     void put(const vec3& v) { put(v.x()); put(v.y()); put(v.z()); }
     void put_hash(std::uint64_t h) { put(double(h & 0xffffffffULL)); put(double(h >> 32)); }
 
+    std::unordered_map<const image_texture*, std::uint64_t> image_hashes;   // one image is shared by many triangles
+
     void image(const image_texture& i)
     {
         put(ARTB_X_IMAGE); put(i.width); put(i.height); put(i.bytes_per_pixel);
-        put_hash(i.data.empty() ? 0 : fnv1a64(i.data.data(), i.data.size()));
+        auto it = image_hashes.find(&i);
+        if (it == image_hashes.end())
+            it = image_hashes.emplace(&i, i.data.empty() ? 0 : fnv1a64(i.data.data(), i.data.size())).first;
+        put_hash(it->second);
     }
     void tex(const texture& t)
     {

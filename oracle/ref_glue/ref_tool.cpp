@@ -85,11 +85,15 @@ struct dumper
             out.push_back(ARTB_X_BARY); v3(bc->color_a); v3(bc->color_b); v3(bc->color_c);
         } else throw std::logic_error("graph dump: unknown texture type");
     }
+    std::map<const image_texture*, std::uint64_t> image_hashes;   // one image is shared by many triangles
     void image(const std::shared_ptr<image_texture>& i)
     {
         out.push_back(ARTB_X_IMAGE);
         out.push_back(i->width); out.push_back(i->height); out.push_back(i->bytes_per_pixel);
-        hash(i->data ? fnv1a(i->data.get(), size_t(i->width) * size_t(i->height) * size_t(i->bytes_per_pixel)) : 0);
+        auto it = image_hashes.find(i.get());
+        if (it == image_hashes.end())
+            it = image_hashes.emplace(i.get(), i->data ? fnv1a(i->data.get(), size_t(i->width) * size_t(i->height) * size_t(i->bytes_per_pixel)) : 0).first;
+        hash(it->second);
     }
     void mat(const std::shared_ptr<material>& m)
     {

@@ -1,0 +1,85 @@
+"""ctypes access to the oracle (oracle/_ref/liboracle_port.so = CPU restatement; oracle/_ref/ref_tool = the
+unmodified reference). TEST INFRASTRUCTURE: imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs only."""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+PORT_LIB = ROOT / "oracle" / "_ref" / "liboracle_port.so"
+REF_TOOL = ROOT / "oracle" / "_ref" / "ref_tool"
+
+HIT_DTYPE = np.dtype([("t", "<f8"), ("p", "<f8", 3), ("normal", "<f8", 3), ("u", "<f8"), ("v", "<f8"),
+                      ("hit", "<i4"), ("prim_id", "<i4"), ("front_face", "<i4"), ("material_type", "<i4")])
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not PORT_LIB.exists():
+            raise ImportError(f"{PORT_LIB} missing: run `make -C oracle port`")
+        lib = C.CDLL(str(PORT_LIB))
+        lib.oracle_scene_build.argtypes = [C.c_int, C.c_char_p]
+        lib.oracle_scene_build.restype = C.c_void_p
+        lib.oracle_scene_free.argtypes = [C.c_void_p]
+        lib.oracle_scene_n_media.argtypes = [C.c_void_p]
+        lib.oracle_scene_n_leaves.argtypes = [C.c_void_p]
+        lib.oracle_rng_next.restype = C.c_double
+        lib.oracle_rng_burn.argtypes = [C.c_long]
+        lib.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_uint64)]
+        lib.oracle_render.restype = C.c_double
+        _lib = lib
+    return _lib
+
+
+class OracleScene:
+    """A scene built by the host mirror and intersected / shaded on the CPU with the reference's algorithm."""
+
+    def __init__(self, alias: int):
+        self.lib = load()
+        self.h = self.lib.oracle_scene_build(int(alias), str(ROOT / "assets").encode())
+        if not self.h:
+            raise RuntimeError("oracle scene build failed")
+        self.n_media = self.lib.oracle_scene_n_media(self.h)
+        self.n_leaves = self.lib.oracle_scene_n_leaves(self.h)
+
+    def trace(self, rays, t_min=0.001, t_max=float("inf"), xi=None, want_xi=False):
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = len(rays)
+        out = np.zeros(n, dtype=HIT_DTYPE)
+        xi_c = np.ascontiguousarray(xi, dtype=np.float64) if xi is not None and self.n_media else None
+        used = np.full((n, self.n_media), np.nan) if want_xi else None
+        rc = self.lib.oracle_trace(self.h, rays.ctypes.data, n, t_min, t_max, xi_c.ctypes.data if xi_c is not None else None,
+                                   used.ctypes.data if used is not None and self.n_media else None, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle_trace failed")
+        return (out, used) if want_xi else out
+
+    def render(self, w, h, spp, max_depth=50, rows=None, burn=0):
+        """single-mode render (engine.h:70-94); returns (rgb8, linear means, elapsed ms, rays)"""
+        if burn:
+            self.lib.oracle_rng_burn(burn)
+        r0, r1 = rows if rows else (0, h)
+        rgb = np.zeros((h, w, 3), dtype=np.uint8)
+        lin = np.zeros((h, w, 3), dtype=np.float64)
+        rays = C.c_uint64(0)
+        ms = self.lib.oracle_render(self.h, w, h, spp, max_depth, r0, r1, rgb.ctypes.data, lin.ctypes.data, C.byref(rays))
+        if ms < 0:
+            raise RuntimeError("oracle_render failed")
+        return rgb, lin, ms, rays.value
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

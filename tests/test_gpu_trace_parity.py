@@ -126,13 +126,19 @@ def test_tmax_and_tmin_window(artb, gpu_ctx, scenes):
     g = np.load(GOLDEN / "trace_6.npz")
     gpu_ctx.upload(scenes(6))
     h = g["hit"].astype(bool)
-    rays, t = g["rays"][h][:512], g["t"][h][:512]
-    # a window ending exactly at the hit still reports it; one ending just before reports something else or a miss
-    for i in range(0, 512, 37):
-        a = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, float(t[i]))
-        assert a["hit"][0] == 1 and a["t"][0] == pytest.approx(t[i], rel=1e-12)
-        b = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, float(np.nextafter(t[i], 0) * (1 - 1e-9)))
-        assert b["hit"][0] == 0 or b["t"][0] < t[i]
+    rays = g["rays"][h][:512:37]
+    full = gpu_ctx.trace_batch(rays, 0.001, float("inf"))
+    assert np.all(full["hit"] == 1)
+    for i in range(len(rays)):
+        t = float(full["t"][i])
+        # a window ending exactly at the hit still reports it ...
+        a = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, t)
+        assert a["hit"][0] == 1 and a["t"][0] == t and a["prim_id"][0] == full["prim_id"][i]
+        # ... one ending one ulp before it does not, and one starting one ulp after it finds something farther
+        b = gpu_ctx.trace_batch(rays[i:i + 1], 0.001, float(np.nextafter(t, 0)))
+        assert b["hit"][0] == 0
+        c = gpu_ctx.trace_batch(rays[i:i + 1], float(np.nextafter(t, np.inf)), float("inf"))
+        assert c["hit"][0] == 0 or c["t"][0] > t
 
 
 def test_empty_batch_and_no_scene(artb):

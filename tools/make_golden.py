@@ -76,9 +76,16 @@ def main():
     OUT.mkdir(parents=True, exist_ok=True)
     info = {"rng_first": [float(x) for x in run("rng", 8).split()],
             "sphere_uv": [[float(x) for x in l.split()] for l in run("uv").splitlines() if l.strip()], "scenes": {}}
-    for alias in range(1, 12):
-        info["scenes"][str(alias)] = last_json(run("info", alias))
+    import hashlib
+    with tempfile.TemporaryDirectory() as tmp:
+        for alias in range(1, 12):
+            info["scenes"][str(alias)] = last_json(run("info", alias))
+            p = os.path.join(tmp, "g.bin")
+            run("graph", alias, p)
+            info["scenes"][str(alias)]["stream_sha256"] = hashlib.sha256(open(p, "rb").read()).hexdigest()
     (OUT / "scene_info.json").write_text(json.dumps(info, indent=1))
+    if "--info-only" in sys.argv:
+        return
     with tempfile.TemporaryDirectory() as tmp:
         for alias, (w, h, stride, spp, max_rays) in TRACE.items():
             p = os.path.join(tmp, "t.bin")
