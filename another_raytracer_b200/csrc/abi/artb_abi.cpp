@@ -31,7 +31,7 @@ struct artb_ctx {
 };
 
 static_assert(sizeof(artb_hit) == sizeof(HitRecordOut), "artb_hit must match the device record");
-static_assert(sizeof(FlatPrim) == 96 && sizeof(FlatNode) == 128 && sizeof(FlatXformOp) == 32 && sizeof(FlatXform) == 8 &&
+static_assert(sizeof(FlatPrim) == 96 && sizeof(FlatNode) == 64 && sizeof(FlatXformOp) == 32 && sizeof(FlatXform) == 8 &&
               sizeof(FlatMaterial) == 48 && sizeof(FlatTexture) == 96 && sizeof(FlatImage) == 24 && sizeof(FlatPerlin) == 9216,
               "flat record sizes are part of the ABI");
 
@@ -216,7 +216,7 @@ int artb_scene_get_flat(const artb_scene* s, artb_flat_scene* out)
     std::memset(out, 0, sizeof(*out));
     out->prims = f.prims.data(); out->n_prims = uint32_t(f.prims.size()); out->n_world_prims = f.n_world_prims;
     out->nodes = f.nodes.data(); out->n_nodes = uint32_t(f.nodes.size());
-    out->root_child = f.root_child; out->root_count = f.root_count; out->bvh_depth = f.bvh_depth;
+    out->root = f.root; out->n_global_prims = f.n_global_prims; out->bvh_depth = f.bvh_depth;
     out->xform_ops = f.xform_ops.data(); out->n_xform_ops = uint32_t(f.xform_ops.size());
     out->xforms = f.xforms.data(); out->n_xforms = uint32_t(f.xforms.size());
     out->materials = f.materials.data(); out->n_materials = uint32_t(f.materials.size());
@@ -244,7 +244,7 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
 {
     if (!ctx || !f) return fail(ctx, ARTB_E_INVALID, "null argument");
     if (f->n_world_prims == 0) return fail(ctx, ARTB_E_EMPTY_SCENE, "Invalid input scene!");
-    if (f->n_world_prims > f->n_prims || (f->n_nodes == 0 && f->root_count <= 0))
+    if (f->n_world_prims > f->n_prims || f->n_global_prims > f->n_world_prims)
         return fail(ctx, ARTB_E_INVALID, "inconsistent flat scene");
     return guarded(ctx, [&]() -> int {
         FlatScene fs;
@@ -263,7 +263,7 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
         copy(fs.texels, f->texels, f->n_texel_bytes);
         copy(fs.perlins, f->perlins, f->n_perlins);
         fs.n_world_prims = f->n_world_prims; fs.n_media = f->n_media;
-        fs.root_child = f->root_child; fs.root_count = f->root_count; fs.bvh_depth = f->bvh_depth;
+        fs.root = f->root; fs.n_global_prims = f->n_global_prims; fs.bvh_depth = f->bvh_depth;
         for (int k = 0; k < 3; ++k) fs.background[k] = f->background[k];
         // bounds-check indices so that a malformed scene cannot make the kernels read out of range
         for (const FlatPrim& p : fs.prims) {
@@ -272,12 +272,14 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
             if (p.type == PRIM_MEDIUM && (p.g[1] < fs.n_world_prims || p.g[1] + p.g[2] > double(fs.prims.size())))
                 throw std::logic_error("flat scene: medium boundary range out of bounds");
         }
-        for (const FlatNode& n : fs.nodes)
-            for (int s = 0; s < 2; ++s) {
-                const int32_t c = s ? n.child1 : n.child0, k = s ? n.count1 : n.count0;
-                if (c < 0 || k < 0 || (k == 0 && size_t(c) >= fs.nodes.size()) || (k > 0 && size_t(c) + size_t(k) > fs.n_world_prims))
-                    throw std::logic_error("flat scene: BVH child out of bounds");
-            }
+        auto check_ref = [&](int32_t ref) {
+            if (ref >= 0) { if (size_t(ref) >= fs.nodes.size()) throw std::logic_error("flat scene: BVH child out of bounds"); return; }
+            const uint32_t code = uint32_t(~ref), first = code >> 3, count = (code & 7u) + 1u;
+            if (first < fs.n_global_prims || size_t(first) + count > fs.n_world_prims)
+                throw std::logic_error("flat scene: BVH leaf out of bounds");
+        };
+        if (fs.n_world_prims > fs.n_global_prims) check_ref(fs.root);
+        for (const FlatNode& n : fs.nodes) { check_ref(n.child0); check_ref(n.child1); }
         for (const FlatXform& x : fs.xforms)
             if (size_t(x.first_op) + x.n_ops > fs.xform_ops.size() || x.n_ops > 8) throw std::logic_error("flat scene: bad transform chain");
         for (const FlatMaterial& m : fs.materials)

@@ -3,7 +3,9 @@
 //
 // The reference's pointer graph (hittable_list / bvh_node / translate / rotate_y / box / primitives /
 // constant_medium, shared_ptr<material>, shared_ptr<texture>) becomes:
-//   prims[]      one fixed-size record per leaf primitive, BVH leaf order first, then media boundaries
+//   prims[]      one fixed-size record per leaf primitive: first the few "global" primitives whose box spans a
+//                large part of the scene (tested for every ray before the traversal: no divergence, and an
+//                early t_max), then the BVH leaves in leaf order, then the media boundaries
 //   nodes[]      one binary BVH over ALL world primitives in WORLD space (instanced primitives keep their
 //                object-space geometry and a transform-chain id; their world boxes bound the transformed
 //                geometry). The closest hit does not depend on the acceleration structure, so this
@@ -43,15 +45,20 @@ struct ARTB_ALIGN(16) FlatPrim {      // 96 B
     uint32_t dfs_id;      // position in the reference's depth-first test order: reported id + tie-break
 };
 
-// Binary BVH node holding BOTH children's boxes, so one 128-byte fetch decides both descents.
-// child >= 0: internal node index. count > 0: leaf, prims[child .. child+count).
-struct ARTB_ALIGN(16) FlatNode {      // 128 B
-    double lo0[3], hi0[3];
-    double lo1[3], hi1[3];
+// Binary BVH node holding BOTH children's boxes, so one 64-byte fetch (four 16-byte loads) decides both
+// descents. Boxes are FLOAT, rounded OUTWARD from the double-precision world boxes: the node test only has
+// to be conservative (it may admit a ray that misses, never reject one that hits), because every candidate
+// primitive is re-tested with the reference's double-precision formula. FP32 slabs issue at twice the FP64
+// rate, need no multi-instruction double min/max, and halve the node bytes.
+// child >= 0: internal node index. child < 0: leaf, code = ~child = (first_prim << 3) | (count - 1).
+struct ARTB_ALIGN(16) FlatNode {      // 64 B
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
     int32_t child0, child1;
-    int32_t count0, count1;
-    int32_t pad[4];
+    int32_t pad[2];
 };
+#define ARTB_MAX_LEAF_PRIMS 8
+#define ARTB_LEAF_CODE(first, count) (~int32_t((uint32_t(first) << 3) | uint32_t((count) - 1)))
 
 enum : uint32_t { XFORM_TRANSLATE = 0, XFORM_ROTATE_Y = 1 };
 
@@ -102,8 +109,8 @@ struct SceneView {
     const FlatImage* images;
     const unsigned char* texels;
     const FlatPerlin* perlins;
-    uint32_t n_prims, n_world_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
-    int32_t root_child, root_count;   // when the world has a single leaf: no nodes at all
+    uint32_t n_prims, n_world_prims, n_global_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
+    int32_t root;                     // root child reference (internal index or leaf code); valid if n_world_prims > n_global_prims
     double background[3];
 };
 

@@ -282,10 +282,12 @@ __global__ void k_after_shade(WaveCounters* c, int cur)
 
 }
 
-// adaptive variance mask: keep the pixels of the current list whose luminance mean is not yet settled
+// adaptive variance mask: keep the pixels of the current list whose luminance mean is not yet settled.
+// The per-sample variance is POOLED over the 3x3 neighbourhood: a pixel whose own first samples all came back
+// black next to neighbours that caught rare bright paths is not declared converged on its own zero variance.
 __global__ void k_adaptive_update(WaveCounters* c, const uint32_t* list, uint32_t* next_list, const float* accum,
-                                  const uint32_t* count, const float* lumsq, uint32_t min_spp, uint32_t max_spp,
-                                  float threshold)
+                                  const uint32_t* count, const float* lumsq, int width, int height, uint32_t min_spp,
+                                  uint32_t max_spp, float threshold)
 {
     const uint32_t n = c->n_list;
     const int lane = threadIdx.x & 31;
@@ -300,11 +302,26 @@ __global__ void k_adaptive_update(WaveCounters* c, const uint32_t* list, uint32_
             if (cnt < max_spp) {
                 keep = true;
                 if (cnt >= min_spp && cnt > 1) {
+                    const int px = int(pixel % uint32_t(width)), py = int(pixel / uint32_t(width));
+                    float sum = 0.f, sumsq = 0.f, nn = 0.f;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int x = px + dx, y = py + dy;
+                            if (x < 0 || y < 0 || x >= width || y >= height) continue;
+                            const uint32_t q = uint32_t(y * width + x);
+                            const float cq = float(count[q]);
+                            if (cq == 0.f) continue;
+                            const float* a = accum + size_t(q) * 3;
+                            sum += 0.2126f * a[0] + 0.7152f * a[1] + 0.0722f * a[2];
+                            sumsq += lumsq[q];
+                            nn += cq;
+                        }
+                    const float pooled_mean = sum / nn;
+                    const float var = fmaxf(sumsq / nn - pooled_mean * pooled_mean, 0.f) * nn / fmaxf(nn - 1.f, 1.f);
                     const float* a = accum + size_t(pixel) * 3;
                     const float mean = (0.2126f * a[0] + 0.7152f * a[1] + 0.0722f * a[2]) / float(cnt);
-                    const float var = fmaxf(lumsq[pixel] / float(cnt) - mean * mean, 0.f) * float(cnt) / float(cnt - 1);
                     const float se = sqrtf(var / float(cnt));
-                    keep = se > threshold * (mean + 0.05f);
+                    keep = se > threshold * (fmaxf(mean, pooled_mean) + 0.05f);
                 }
             }
         }
@@ -465,8 +482,8 @@ void Renderer::upload(const FlatScene& fs)
     v.n_xforms = uint32_t(fs.xforms.size());
     v.n_materials = uint32_t(fs.materials.size());
     v.n_textures = uint32_t(fs.textures.size());
-    v.root_child = fs.root_child;
-    v.root_count = fs.root_count;
+    v.n_global_prims = fs.n_global_prims;
+    v.root = fs.root;
     for (int k = 0; k < 3; ++k) v.background[k] = fs.background[k];
     CUDA_CHECK(cudaStreamSynchronize(st));
     view_ = v;
@@ -661,7 +678,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
             issued_total += I.counters_host->total;
             first += batch;
             if (first - uint32_t(p.sample_begin) >= max_spp) break;
-            k_adaptive_update<<<I.sm_count * 4, 256, 0, st>>>(w.c, list, I.list[flip], accum_dev, count_dev, I.lumsq,
+            k_adaptive_update<<<I.sm_count * 4, 256, 0, st>>>(w.c, list, I.list[flip], accum_dev, count_dev, I.lumsq, p.width, p.height,
                                                               uint32_t(p.adaptive_min_spp), max_spp, float(p.adaptive_threshold));
             S.launches++;
             CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));

@@ -178,11 +178,11 @@ __device__ inline bool medium_t(const SceneView& s, const FlatPrim& p, const DRa
 // ---- BVH traversal ------------------------------------------------------------------------------
 struct ClosestHit { double t; int32_t prim; uint32_t dfs; };
 
-__device__ __forceinline__ void test_leaf(const SceneView& s, int32_t first, int32_t count, const DRay& world,
-                                          double t_min, const MediumXi& xi, ClosestHit& best,
-                                          uint32_t& cached_xform, DRay& cached_ray)
+__device__ __forceinline__ void test_prims(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                                           double t_min, const MediumXi& xi, ClosestHit& best,
+                                           uint32_t& cached_xform, DRay& cached_ray)
 {
-    for (int32_t i = first; i < first + count; ++i) {
+    for (uint32_t i = first; i < first + count; ++i) {
         const FlatPrim& p = s.prims[i];
         double t;
         bool ok;
@@ -193,24 +193,63 @@ __device__ __forceinline__ void test_leaf(const SceneView& s, int32_t first, int
             ok = surface_t(p, cached_ray, t_min, best.t, t);
         }
         if (ok && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
-            best.t = t; best.prim = i; best.dfs = p.dfs_id;
+            best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
         }
     }
 }
 
-// slab test against [t_min, t_best]; NaNs (0 * inf) are ignored by fmin/fmax exactly as the reference's
-// comparisons ignore them (aabb.h:22-23). Inclusive, so equal-t candidates are still visited.
-__device__ __forceinline__ bool slab(const double* lo, const double* hi, d3 o, d3 inv, double t_min, double t_best, double& enter)
+// Conservative FP32 slab test. The ray is held as inv = fl(1/d) (magnitude clamped to 1e30, so no inf/NaN ever
+// appears) and, per axis, c = fl(o)*inv with an absolute pad |c|*2^-22 that covers the rounding of the origin to
+// float, of c itself and of the fused multiply-add; the near plane subtracts c+pad, the far plane c-pad. A final
+// relative widening by 2^-21 covers the rounding of inv and of the node planes (which the flattener already rounds
+// OUTWARD). The interval can only grow, never shrink: a ray that hits the double-precision box always passes, and
+// since every candidate primitive is then tested in double with the reference's formula, results do not depend on
+// this test at all — only the amount of work does. Inclusive comparison, so equal-t candidates are still visited.
+struct SlabRay {
+    float ix, iy, iz;        // 1/d
+    float nx, ny, nz;        // c + pad  (subtracted on the near plane)
+    float fx, fy, fz;        // c - pad  (subtracted on the far plane)
+    bool px, py, pz;         // direction sign >= 0: near plane is lo
+};
+
+__device__ __forceinline__ void slab_axis(double o, double d, float& inv, float& cn, float& cf, bool& pos)
 {
-    const double x0 = (lo[0] - o.x) * inv.x, x1 = (hi[0] - o.x) * inv.x;
-    const double y0 = (lo[1] - o.y) * inv.y, y1 = (hi[1] - o.y) * inv.y;
-    const double z0 = (lo[2] - o.z) * inv.z, z1 = (hi[2] - o.z) * inv.z;
-    const double tn = fmax(fmax(fmin(x0, x1), fmin(y0, y1)), fmax(fmin(z0, z1), t_min));
-    const double tf = fmin(fmin(fmax(x0, x1), fmax(y0, y1)), fmin(fmax(z0, z1), t_best));
+    double id = 1.0 / d;
+    id = fmin(fmax(id, -1e30), 1e30);
+    if (!(id == id)) id = 1e30;
+    inv = float(id);
+    pos = inv >= 0.f;
+    const float c = float(o) * inv;
+    const float pad = fabsf(c) * 2.384185791015625e-07f + 1e-30f;   // 2^-22
+    cn = c + pad;
+    cf = c - pad;
+}
+
+__device__ __forceinline__ SlabRay make_slab_ray(const DRay& r)
+{
+    SlabRay s;
+    slab_axis(r.o.x, r.d.x, s.ix, s.nx, s.fx, s.px);
+    slab_axis(r.o.y, r.d.y, s.iy, s.ny, s.fy, s.py);
+    slab_axis(r.o.z, r.d.z, s.iz, s.nz, s.fz, s.pz);
+    return s;
+}
+
+__device__ __forceinline__ bool slab(const float* lo, const float* hi, const SlabRay& r, float t_min, float t_best, float& enter)
+{
+    const float nx = fmaf(r.px ? lo[0] : hi[0], r.ix, -r.nx), fx = fmaf(r.px ? hi[0] : lo[0], r.ix, -r.fx);
+    const float ny = fmaf(r.py ? lo[1] : hi[1], r.iy, -r.ny), fy = fmaf(r.py ? hi[1] : lo[1], r.iy, -r.fy);
+    const float nz = fmaf(r.pz ? lo[2] : hi[2], r.iz, -r.nz), fz = fmaf(r.pz ? hi[2] : lo[2], r.iz, -r.fz);
+    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_min));
+    float tf = fminf(fminf(fx, fy), fminf(fz, t_best));
+    tn -= fabsf(tn) * 4.76837158203125e-07f;    // 2^-21
+    tf += fabsf(tf) * 4.76837158203125e-07f;
     enter = tn;
     return tn <= tf;
 }
 
+// "while-while" traversal (Aila & Laine 2009): an inner loop that only walks internal nodes until this lane holds
+// a leaf, then an inner loop that only intersects primitives. The lanes of a warp re-converge between the two, so
+// node tests run next to node tests and primitive tests next to primitive tests.
 __device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi)
 {
     ClosestHit best;
@@ -218,36 +257,44 @@ __device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, do
     uint32_t cached_xform = 0;
     DRay cached_ray = ray;
 
-    if (s.root_count > 0) {
-        test_leaf(s, s.root_child, s.root_count, ray, t_min, xi, best, cached_xform, cached_ray);
-        return best;
-    }
-    if (s.n_world_prims == 0) return best;
+    // global primitives first: same work for every lane, and an early t_max for the traversal
+    if (s.n_global_prims) test_prims(s, 0, s.n_global_prims, ray, t_min, xi, best, cached_xform, cached_ray);
+    if (s.n_world_prims == s.n_global_prims) return best;
 
-    const d3 inv = mk3(1.0 / ray.d.x, 1.0 / ray.d.y, 1.0 / ray.d.z);
+    const SlabRay sr = make_slab_ray(ray);
+    const float t_min_f = __double2float_rd(t_min);
+    float t_best_f = __double2float_ru(best.t);
+
     int32_t stack[ARTB_STACK_DEPTH];
     int sp = 0;
-    int32_t node = s.root_child;
-    while (true) {
-        const FlatNode& n = s.nodes[node];
-        double e0, e1;
-        const bool h0 = slab(n.lo0, n.hi0, ray.o, inv, t_min, best.t, e0);
-        const bool h1 = slab(n.lo1, n.hi1, ray.o, inv, t_min, best.t, e1);
-        int32_t next = -1;
-        if (h0 && n.count0 > 0) test_leaf(s, n.child0, n.count0, ray, t_min, xi, best, cached_xform, cached_ray);
-        if (h1 && n.count1 > 0) test_leaf(s, n.child1, n.count1, ray, t_min, xi, best, cached_xform, cached_ray);
-        const bool i0 = h0 && n.count0 == 0, i1 = h1 && n.count1 == 0;
-        if (i0 && i1) {
-            const bool first0 = e0 <= e1;
-            next = first0 ? n.child0 : n.child1;
-            if (sp < ARTB_STACK_DEPTH) stack[sp++] = first0 ? n.child1 : n.child0;
-        } else if (i0) next = n.child0;
-        else if (i1) next = n.child1;
-        if (next < 0) {
-            if (sp == 0) break;
-            next = stack[--sp];
+    int32_t cur = s.root;            // >= 0 internal node, < 0 leaf code
+    const int32_t kDone = 0x7fffffff;
+    while (cur != kDone) {
+        // ---- walk internal nodes until a leaf is in hand
+        while (cur >= 0 && cur != kDone) {
+            const float4* q = reinterpret_cast<const float4*>(s.nodes + cur);
+            const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+            const float lo0[3] = { a.x, a.y, a.z }, hi0[3] = { a.w, b.x, b.y };
+            const float lo1[3] = { b.z, b.w, c.x }, hi1[3] = { c.y, c.z, c.w };
+            const int32_t c0 = __float_as_int(d.x), c1 = __float_as_int(d.y);
+            float e0, e1;
+            const bool h0 = slab(lo0, hi0, sr, t_min_f, t_best_f, e0);
+            const bool h1 = slab(lo1, hi1, sr, t_min_f, t_best_f, e1);
+            if (h0 && h1) {
+                const bool first0 = e0 <= e1;
+                cur = first0 ? c0 : c1;
+                if (sp < ARTB_STACK_DEPTH) stack[sp++] = first0 ? c1 : c0;
+            } else if (h0) cur = c0;
+            else if (h1) cur = c1;
+            else cur = sp ? stack[--sp] : kDone;
         }
-        node = next;
+        // ---- intersect the leaf
+        if (cur != kDone) {
+            const uint32_t code = uint32_t(~cur);
+            test_prims(s, code >> 3, (code & 7u) + 1u, ray, t_min, xi, best, cached_xform, cached_ray);
+            t_best_f = __double2float_ru(best.t);
+            cur = sp ? stack[--sp] : kDone;
+        }
     }
     return best;
 }

@@ -2,6 +2,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -418,45 +419,85 @@ private:
         return me;
     }
 
-    int emit_node(int t)   // internal tnode -> FlatNode index
+    static float round_down(double x)
+    {
+        float f = float(x);
+        if (double(f) > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity());
+        return f;
+    }
+    static float round_up(double x)
+    {
+        float f = float(x);
+        if (double(f) < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity());
+        return f;
+    }
+
+    int32_t child_ref(int t, uint32_t prim_base)   // tnode -> internal node index or leaf code
+    {
+        const TNode& k = tnodes[size_t(t)];
+        if (k.left < 0) return ARTB_LEAF_CODE(prim_base + uint32_t(k.first), k.count);
+        return emit_node(t, prim_base);
+    }
+
+    int emit_node(int t, uint32_t prim_base)   // internal tnode -> FlatNode index
     {
         const int me = int(out.nodes.size());
         out.nodes.emplace_back();
         std::memset(&out.nodes[size_t(me)], 0, sizeof(FlatNode));
         const int kids[2] = { tnodes[size_t(t)].left, tnodes[size_t(t)].right };
         for (int s = 0; s < 2; ++s) {
+            const int32_t ref = child_ref(kids[s], prim_base);
             const TNode& k = tnodes[size_t(kids[s])];
-            int child, cnt;
-            if (k.left < 0) { child = k.first; cnt = k.count; }
-            else            { child = emit_node(kids[s]); cnt = 0; }
             FlatNode& n = out.nodes[size_t(me)];   // re-fetch: the vector may have grown
-            double* lo = s == 0 ? n.lo0 : n.lo1;
-            double* hi = s == 0 ? n.hi0 : n.hi1;
-            for (int a = 0; a < 3; ++a) { lo[a] = k.box.lo[a]; hi[a] = k.box.hi[a]; }
-            (s == 0 ? n.child0 : n.child1) = child;
-            (s == 0 ? n.count0 : n.count1) = cnt;
+            float* lo = s == 0 ? n.lo0 : n.lo1;
+            float* hi = s == 0 ? n.hi0 : n.hi1;
+            for (int a = 0; a < 3; ++a) { lo[a] = round_down(k.box.lo[a]); hi[a] = round_up(k.box.hi[a]); }
+            (s == 0 ? n.child0 : n.child1) = ref;
         }
         return me;
     }
 
     void build_bvh()
     {
+        // 1. global primitives: boxes that span a large share of the scene are pulled out of the tree
+        std::vector<Item> globals, rest = world_items;
+        for (int pass = 0; pass < 4 && int(globals.size()) < opt.max_global_prims; ++pass) {
+            Box3 all;
+            for (const Item& it : rest) all.grow(it.box);
+            if (rest.size() <= 1 || !(all.half_area() > 0)) break;
+            std::vector<Item> keep;
+            bool moved = false;
+            for (const Item& it : rest) {
+                if (int(globals.size()) < opt.max_global_prims && it.box.half_area() >= opt.global_area_fraction * all.half_area()) {
+                    globals.push_back(it); moved = true;
+                } else keep.push_back(it);
+            }
+            rest.swap(keep);
+            if (!moved) break;
+        }
+        if (world_items.size() <= size_t(opt.max_global_prims)) { globals = world_items; rest.clear(); }   // tiny scene: a plain list
+        out.n_global_prims = uint32_t(globals.size());
+        out.n_world_prims = uint32_t(world_items.size());
+        Box3 whole;
+        for (const Item& it : world_items) whole.grow(it.box);
+        for (int k = 0; k < 3; ++k) { out.world_lo[k] = whole.valid() ? whole.lo[k] : 0; out.world_hi[k] = whole.valid() ? whole.hi[k] : 0; }
+        // globals keep the reference's test order (dfs), which makes early best-t pruning deterministic
+        std::sort(globals.begin(), globals.end(), [](const Item& a, const Item& b) { return a.prim.dfs_id < b.prim.dfs_id; });
+        out.prims.reserve(world_items.size() + boundary_items.size());
+        for (const Item& it : globals) out.prims.push_back(it.prim);
+
+        // 2. binned-SAH tree over the rest
+        world_items.swap(rest);
         const int n = int(world_items.size());
-        out.n_world_prims = uint32_t(n);
-        if (n == 0) { out.root_child = 0; out.root_count = 0; return; }
+        out.root = 0;
+        if (n == 0) return;
+        if (opt.max_leaf_prims > ARTB_MAX_LEAF_PRIMS) throw std::logic_error("flatten: max_leaf_prims exceeds ARTB_MAX_LEAF_PRIMS");
         order.resize(size_t(n));
         for (int i = 0; i < n; ++i) order[size_t(i)] = i;
         tnodes.reserve(size_t(2 * n));
         const int root = build_range(0, n, 0);
-        out.prims.reserve(size_t(n) + boundary_items.size());
         for (int i = 0; i < n; ++i) out.prims.push_back(world_items[size_t(order[size_t(i)])].prim);
-        for (int k = 0; k < 3; ++k) { out.world_lo[k] = tnodes[size_t(root)].box.lo[k]; out.world_hi[k] = tnodes[size_t(root)].box.hi[k]; }
-        if (tnodes[size_t(root)].left < 0) {
-            out.root_child = 0; out.root_count = n;   // a single leaf: no nodes
-        } else {
-            out.root_child = emit_node(root);
-            out.root_count = 0;
-        }
+        out.root = child_ref(root, out.n_global_prims);
     }
 };
 

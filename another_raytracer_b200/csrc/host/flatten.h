@@ -26,7 +26,7 @@
 namespace artb {
 
 struct FlatScene {
-    std::vector<FlatPrim> prims;          // [0, n_world_prims) in BVH leaf order, then boundary prims
+    std::vector<FlatPrim> prims;          // [0,n_global) global prims, [n_global,n_world) BVH leaf order, then boundary prims
     std::vector<FlatNode> nodes;
     std::vector<FlatXformOp> xform_ops;
     std::vector<FlatXform> xforms;        // [0] = identity
@@ -36,17 +36,20 @@ struct FlatScene {
     std::vector<unsigned char> texels;
     std::vector<FlatPerlin> perlins;
     uint32_t n_world_prims = 0;
+    uint32_t n_global_prims = 0;
     uint32_t n_media = 0;
     uint32_t n_leaves_total = 0;          // dfs ids handed out (reachable or not)
     uint32_t n_culled = 0;
-    int32_t root_child = 0, root_count = 0;
+    int32_t root = 0;                     // internal node index or leaf code (flat_scene.h)
     double background[3] = {0, 0, 0};
     double world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     int bvh_depth = 0;
 };
 
 struct FlattenOptions {
-    int max_leaf_prims = 4;
+    int max_leaf_prims = 4;               // <= ARTB_MAX_LEAF_PRIMS
+    double global_area_fraction = 0.25;   // prims whose box half-area exceeds this share of the scene's go to the global list
+    int max_global_prims = 8;
     int sah_bins = 16;
     double traversal_cost = 1.0;
     double intersect_cost = 1.5;

@@ -63,8 +63,14 @@ def test_known_structure_numbers(artb):
 
 
 PRIM = np.dtype([("g", "<f8", 10), ("type", "<u4"), ("material", "<u4"), ("xform", "<u4"), ("dfs_id", "<u4")])
-NODE = np.dtype([("lo0", "<f8", 3), ("hi0", "<f8", 3), ("lo1", "<f8", 3), ("hi1", "<f8", 3),
-                 ("child0", "<i4"), ("child1", "<i4"), ("count0", "<i4"), ("count1", "<i4"), ("pad", "<i4", 4)])
+NODE = np.dtype([("lo0", "<f4", 3), ("hi0", "<f4", 3), ("lo1", "<f4", 3), ("hi1", "<f4", 3),
+                 ("child0", "<i4"), ("child1", "<i4"), ("pad", "<i4", 2)])
+
+
+def leaf_range(ref):
+    """child reference < 0 -> (first prim, count); see ARTB_LEAF_CODE in csrc/device/flat_scene.h"""
+    code = (~int(ref)) & 0xFFFFFFFF
+    return code >> 3, (code & 7) + 1
 
 
 def _flat_arrays(scene):
@@ -79,28 +85,29 @@ def _flat_arrays(scene):
 def test_flattened_bvh_invariants(artb, alias):
     s = artb.Scene.build(alias)
     v, prims, nodes = _flat_arrays(s)
-    assert PRIM.itemsize == 96 and NODE.itemsize == 128
-    n_world = v.n_world_prims
-    # every world primitive is referenced by exactly one leaf; dfs ids are unique
+    assert PRIM.itemsize == 96 and NODE.itemsize == 64
+    n_world, n_global = v.n_world_prims, v.n_global_prims
+    # every world primitive is either global or referenced by exactly one leaf; dfs ids are unique
     seen = np.zeros(n_world, dtype=int)
+    seen[:n_global] += 1
     depth = 0
-    if v.root_count > 0:
-        seen[v.root_child:v.root_child + v.root_count] += 1
-    else:
-        stack = [(v.root_child, 1)]
+    if n_world > n_global:
+        stack = [(v.root, 0)]
         while stack:
-            i, d = stack.pop()
+            ref, d = stack.pop()
             depth = max(depth, d)
-            n = nodes[i]
-            for c, k in ((n["child0"], n["count0"]), (n["child1"], n["count1"])):
-                if k > 0:
-                    seen[c:c + k] += 1
-                else:
-                    stack.append((int(c), d + 1))
+            if ref < 0:
+                first, count = leaf_range(ref)
+                assert first >= n_global and count <= 8
+                seen[first:first + count] += 1
+            else:
+                stack.append((int(nodes[ref]["child0"]), d + 1))
+                stack.append((int(nodes[ref]["child1"]), d + 1))
     assert np.all(seen == 1)
     assert depth <= s.info["bvh_depth"] + 1 < 63
     assert len(np.unique(prims["dfs_id"])) == len(prims)
     assert prims["dfs_id"].max() < s.info["n_leaves_total"]
+    assert np.all(np.diff(prims["dfs_id"][:n_global].astype(np.int64)) > 0)      # globals keep the reference's order
     # media point at boundary ranges behind the world primitives
     for p in prims[:n_world][prims["type"][:n_world] == 6]:
         first, count = int(p["g"][1]), int(p["g"][2])
@@ -108,8 +115,23 @@ def test_flattened_bvh_invariants(artb, alias):
     assert np.all(prims["type"][n_world:] != 6)
 
 
+def test_global_primitive_lists(artb):
+    """scene-spanning primitives are tested up front: the ground sphere of scene 1, the mist of scene 8; tiny scenes
+    (Cornell box: 18 rects) have no tree at all above a handful of primitives"""
+    s1 = artb.Scene.build(1)
+    v, prims, _ = _flat_arrays(s1)
+    assert v.n_global_prims >= 1 and prims["g"][0][3] == 1000.0
+    s8 = artb.Scene.build(8)
+    v, prims, _ = _flat_arrays(s8)
+    g = prims[:v.n_global_prims]
+    assert np.any(g["type"] == 6)
+    s2 = artb.Scene.build(2)
+    v, _, nodes = _flat_arrays(s2)
+    assert v.n_global_prims == v.n_world_prims == 2 and len(nodes) == 0
+
+
 def test_child_boxes_bound_their_primitives(artb):
-    """node boxes contain the (untransformed) primitives below them — checked on the identity-transform random scene"""
+    """float node boxes (rounded outward) contain the double-precision primitives below them — random scene, identity transforms"""
     s = artb.Scene.build(1)
     v, prims, nodes = _flat_arrays(s)
 
@@ -120,20 +142,20 @@ def test_child_boxes_bound_their_primitives(artb):
         c0, c1, r = g[0:3], g[3:6], g[8]
         return np.minimum(c0, c1) - r, np.maximum(c0, c1) + r
 
-    def check(i):
-        n = nodes[i]
+    def bounds(ref):
+        if ref < 0:
+            first, count = leaf_range(ref)
+            boxes = [prim_box(p) for p in prims[first:first + count]]
+            return np.min([b[0] for b in boxes], axis=0), np.max([b[1] for b in boxes], axis=0)
+        n = nodes[ref]
         lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
-        for lo_c, hi_c, c, k in ((n["lo0"], n["hi0"], n["child0"], n["count0"]), (n["lo1"], n["hi1"], n["child1"], n["count1"])):
-            if k > 0:
-                boxes = [prim_box(p) for p in prims[c:c + k]]
-                l = np.min([b[0] for b in boxes], axis=0); h = np.max([b[1] for b in boxes], axis=0)
-            else:
-                l, h = check(int(c))
-            assert np.all(lo_c <= l) and np.all(hi_c >= h)
-            lo = np.minimum(lo, lo_c); hi = np.maximum(hi, hi_c)
+        for lo_c, hi_c, c in ((n["lo0"], n["hi0"], n["child0"]), (n["lo1"], n["hi1"], n["child1"])):
+            l, h = bounds(int(c))
+            assert np.all(lo_c.astype(np.float64) <= l) and np.all(hi_c.astype(np.float64) >= h)
+            lo = np.minimum(lo, l); hi = np.maximum(hi, h)
         return lo, hi
 
-    check(v.root_child)
+    bounds(v.root)
 
 
 def test_zero_thickness_bvh_boxes_are_culled(artb):
