@@ -558,6 +558,10 @@ ORACLE_API int oracle_scene_n_media(void* h) { return static_cast<oracle_scene*>
 ORACLE_API int oracle_scene_n_leaves(void* h) { return static_cast<oracle_scene*>(h)->n_leaves; }
 ORACLE_API double oracle_rng_next() { return random_double(); }
 ORACLE_API void oracle_rng_burn(long n) { for (long i = 0; i < n; ++i) random_double(); }
+// Re-seed the render stream AFTER the scene is built (the scene itself always comes from the default seed, like the
+// reference's). The reference has no seed API; independent sample sets for noise estimates need streams that do not
+// overlap, which offsets into one stream cannot give once a render consumes more draws than the offset.
+ORACLE_API void oracle_rng_reseed(unsigned seed) { reset_global_rng(seed); }
 
 // closest hit for explicit rays; xi: n x n_media table (NULL: media draw from the global stream, in list order,
 // exactly like the reference); xi_used (optional): receives the xi each medium consumed

@@ -29,6 +29,7 @@ def load():
         lib.oracle_scene_n_leaves.argtypes = [C.c_void_p]
         lib.oracle_rng_next.restype = C.c_double
         lib.oracle_rng_burn.argtypes = [C.c_long]
+        lib.oracle_rng_reseed.argtypes = [C.c_uint]
         lib.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_uint64)]
@@ -60,8 +61,11 @@ class OracleScene:
             raise RuntimeError("oracle_trace failed")
         return (out, used) if want_xi else out
 
-    def render(self, w, h, spp, max_depth=50, rows=None, burn=0):
-        """single-mode render (engine.h:70-94); returns (rgb8, linear means, elapsed ms, rays)"""
+    def render(self, w, h, spp, max_depth=50, rows=None, burn=0, reseed=None):
+        """single-mode render (engine.h:70-94); returns (rgb8, linear means, elapsed ms, rays). `burn` skips draws of
+        the reference stream (what SURVEY 8c does); `reseed` starts an independent MT19937 stream after the scene build."""
+        if reseed is not None:
+            self.lib.oracle_rng_reseed(int(reseed))
         if burn:
             self.lib.oracle_rng_burn(burn)
         r0, r1 = rows if rows else (0, h)

@@ -2,8 +2,8 @@
 """Converged oracle images for the PSNR gate (tests/golden/converged_<alias>_<W>x<H>.npz).
 
 Uses the C++ restatement of the reference (oracle/port, pinned bit-identical to the unmodified reference by
-tests/test_oracle_port.py) in `procs` processes with different offsets into the reference RNG stream, and averages the
-per-pixel float64 means — the reference itself would need hours single-threaded for the same sample count."""
+tests/test_oracle_port.py) in `procs` processes, each re-seeding the reference's MT19937 after the scene build (independent streams), and
+averages the per-pixel float64 means — the reference itself would need hours single-threaded for the same sample count."""
 import multiprocessing as mp
 import sys
 import time
@@ -20,10 +20,10 @@ JOBS = [  # alias, W, H, total spp
 
 
 def work(args):
-    alias, w, h, spp, burn = args
+    alias, w, h, spp, seed = args
     import oracle_lib as O
     s = O.OracleScene(alias)
-    _, lin, ms, rays = s.render(w, h, spp, burn=burn)
+    _, lin, ms, rays = s.render(w, h, spp, reseed=seed)      # independent, non-overlapping streams
     return lin, rays
 
 
@@ -34,7 +34,7 @@ def main():
         t = time.time()
         each = spp // procs
         with mp.Pool(procs) as pool:
-            res = pool.map(work, [(alias, w, h, each, 100003 * (i + 1)) for i in range(procs)])
+            res = pool.map(work, [(alias, w, h, each, 90001 + 7919 * i) for i in range(procs)])
         lin = np.mean([r[0] for r in res], axis=0)
         half_a = np.mean([r[0] for r in res[: procs // 2]], axis=0)
         half_b = np.mean([r[0] for r in res[procs // 2:]], axis=0)
