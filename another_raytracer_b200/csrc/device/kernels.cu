@@ -184,7 +184,10 @@ __global__ void k_after_generate(WaveCounters* c, int cur)
     c->cursor = 0;
 }
 
-__global__ void __launch_bounds__(128) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+#ifndef ARTB_EXTEND_MIN_BLOCKS
+#define ARTB_EXTEND_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, ARTB_EXTEND_MIN_BLOCKS) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
 {
     WaveCounters* c = w.c;
     const uint32_t n = c->n_extend[cur];
