@@ -264,6 +264,13 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
         copy(fs.perlins, f->perlins, f->n_perlins);
         fs.n_world_prims = f->n_world_prims; fs.n_media = f->n_media;
         fs.root = f->root; fs.n_global_prims = f->n_global_prims; fs.bvh_depth = f->bvh_depth;
+        // every constant_medium must sit at the END of the global range (the device tests media after the traversal)
+        for (uint32_t i = 0; i < fs.n_world_prims; ++i) {
+            const bool is_medium = fs.prims[i].type == PRIM_MEDIUM;
+            if (is_medium && i >= fs.n_global_prims) throw std::logic_error("flat scene: a constant_medium outside the global range");
+            if (is_medium) fs.n_global_media++;
+            else if (fs.n_global_media && i < fs.n_global_prims) throw std::logic_error("flat scene: global media must come last");
+        }
         for (int k = 0; k < 3; ++k) fs.background[k] = f->background[k];
         // bounds-check indices so that a malformed scene cannot make the kernels read out of range
         for (const FlatPrim& p : fs.prims) {

@@ -110,6 +110,7 @@ struct SceneView {
     const unsigned char* texels;
     const FlatPerlin* perlins;
     uint32_t n_prims, n_world_prims, n_global_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
+    uint32_t n_global_media;          // media among the global primitives (tested after the traversal)
     int32_t root;                     // root child reference (internal index or leaf code); valid if n_world_prims > n_global_prims
     double background[3];
 };

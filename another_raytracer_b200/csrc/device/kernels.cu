@@ -3,17 +3,17 @@
 // Pipeline (one "wave" = every live path advances by one bounce), replacing the recursion of
 // engine::_ray_color (engine.h:447-466) and the pixel/sample loops of engine::_run_single (engine.h:58-94):
 //
-//   k_generate   free path slots take the next (pixel, sample): jitter + camera::get_ray -> ray queue
+//   k_shade      one warp = 32 entries of ONE queue: 32 hits of one material type (hit record, texture, emitted,
+//                scatter) or 32 free slots that start the next (pixel, sample): jitter + camera::get_ray. Paths
+//                that end (light, absorbed, depth 50) add their radiance and free the slot; scattered and fresh
+//                rays are queued for the extend kernel
 //   k_extend     closest hit per queued ray (rt_intersect.cuh); misses add the background and free the
 //                slot; hits are binned BY MATERIAL TYPE into per-material queues (warp-aggregated appends)
-//   k_shade      one warp = 32 hits of ONE material type: hit record, texture, emitted, scatter; paths that
-//                end (light, absorbed, depth 50) add their radiance and free the slot, the others queue the
-//                scattered ray for the next wave
 //   k_resolve    write_color (color.h:6-22): mean, gamma 2, clamp, 8-bit
 //
 // Path state lives in HBM as three arrays of sector-sized records indexed by slot (ray 64 B, aux 32 B,
-// hit 16 B), so a queue-indexed gather wastes no bytes of a 32 B sector. No kernel waits on another one;
-// queue counters are reset by two single-thread housekeeping kernels per wave, all on one stream.
+// hit 16 B), so a queue-indexed gather wastes no bytes of a 32 B sector. Two launches per wave on one stream;
+// no kernel waits on another one and the queue counters are reset inside the kernels (see WaveCounters).
 #include "renderer.h"
 #include "rt_shade.cuh"
 
@@ -30,10 +30,19 @@ struct __align__(16) PathRay { double o[3], d[3], tm, pad; };                   
 struct __align__(16) PathAux { float thr[3]; uint32_t pixel, sample, rng_block, depth, pad; };   // 32 B
 struct __align__(16) PathHit { double t; int32_t prim; int32_t pad; };              // 16 B
 
+// Queues written by k_extend (one per material type + the free-slot list) and their counters. Counters are
+// double-buffered by wave parity so that each kernel can reset, from one thread, the counters that NEITHER it nor
+// any concurrently running kernel touches — no separate housekeeping launches:
+//   k_shade(cur)   consumes n_out[cur][*], appends to n_extend[cur^1] and n_out[cur^1][Q_REGEN];
+//                  resets n_extend[cur], n_out[cur^1][0..MAT_COUNT) and the chunk cursor
+//   k_extend(cur)  consumes n_extend[cur], appends to n_out[cur][*];
+//                  resets n_out[cur^1][Q_REGEN] (after adding it to `issued`) and counts the rays
+#define Q_REGEN MAT_COUNT
+#define Q_OUT_COUNT (MAT_COUNT + 1)
+
 struct WaveCounters {
     uint32_t n_extend[2];
-    uint32_t n_regen[2];
-    uint32_t n_shade[MAT_COUNT];
+    uint32_t n_out[2][Q_OUT_COUNT];
     uint32_t cursor;
     uint32_t n_list;                  // pixels in the current round's list
     uint32_t n_next_list;             // adaptive: pixels still unconverged
@@ -46,7 +55,7 @@ struct WaveBuffers {
     PathHit* hits;
     uint32_t* q_extend[2];
     uint32_t* q_regen[2];
-    uint32_t* q_shade[MAT_COUNT];
+    uint32_t* q_shade;                // MAT_COUNT queues of `pool` entries, back to back
     WaveCounters* c;
     uint32_t pool;
 };
@@ -75,6 +84,19 @@ __device__ __forceinline__ void queue_push(uint32_t* q, uint32_t* count, bool pr
     if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
 }
 
+// Append to one of SEVERAL queues with a single round trip to the counters: lanes that target the same queue
+// (same key) elect a leader, and all leaders issue their atomicAdd in the same instruction. key < 0: no append.
+// Returns the lane's position in its queue.
+__device__ __forceinline__ uint32_t multi_queue_reserve(int key, uint32_t* counter, int lane)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (key >= 0 && lane == leader) base = atomicAdd(counter, uint32_t(__popc(peers)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
+}
+
 __device__ __forceinline__ DRay load_ray(const PathRay* rays, uint32_t slot)
 {
     const double2* p = reinterpret_cast<const double2*>(rays + slot);
@@ -93,6 +115,18 @@ __device__ __forceinline__ void store_ray(PathRay* rays, uint32_t slot, const DR
     p[1] = make_double2(r.o.z, r.d.x);
     p[2] = make_double2(r.d.y, r.d.z);
     p[3] = make_double2(r.tm, 0.0);
+}
+
+__device__ __forceinline__ void load_aux(const PathAux* aux, uint32_t slot, PathAux& a)
+{
+    *reinterpret_cast<uint4*>(&a) = *reinterpret_cast<const uint4*>(aux + slot);
+    *(reinterpret_cast<uint4*>(&a) + 1) = *(reinterpret_cast<const uint4*>(aux + slot) + 1);
+}
+
+__device__ __forceinline__ void store_aux(PathAux* aux, uint32_t slot, const PathAux& a)
+{
+    *reinterpret_cast<uint4*>(aux + slot) = *reinterpret_cast<const uint4*>(&a);
+    *(reinterpret_cast<uint4*>(aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
 }
 
 __device__ __forceinline__ void add_radiance(const RoundParams& rp, uint32_t pixel, float r, float g, float b)
@@ -116,8 +150,9 @@ __global__ void k_init_pool(WaveBuffers w)
     if (i == 0) {
         WaveCounters* c = w.c;
         c->n_extend[0] = c->n_extend[1] = 0;
-        c->n_regen[0] = w.pool; c->n_regen[1] = 0;
-        for (int m = 0; m < MAT_COUNT; ++m) c->n_shade[m] = 0;
+        for (int k = 0; k < 2; ++k)
+            for (int m = 0; m < Q_OUT_COUNT; ++m) c->n_out[k][m] = 0;
+        c->n_out[0][Q_REGEN] = w.pool;
         c->cursor = 0; c->n_list = 0; c->n_next_list = 0;
         c->issued = c->total = c->rays = c->finished = 0;
     }
@@ -133,64 +168,20 @@ __global__ void k_round_begin(WaveCounters* c, long long n_list_fixed, uint32_t 
     c->total = (unsigned long long)n * batch;
 }
 
-__global__ void __launch_bounds__(256) k_generate(WaveBuffers w, RoundParams rp, int cur)
-{
-    WaveCounters* c = w.c;
-    const uint32_t n = c->n_regen[cur];
-    const unsigned long long issued = c->issued, total = c->total;
-    const uint32_t n_list = c->n_list;
-    const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
-        const uint32_t i = base + lane;
-        const bool valid = i < n;
-        uint32_t slot = 0;
-        bool spawned = false;
-        if (valid) {
-            slot = w.q_regen[cur][i];
-            const unsigned long long s = issued + i;
-            if (s < total) {
-                spawned = true;
-                const uint32_t li = uint32_t(s % n_list);
-                const uint32_t k = uint32_t(s / n_list);
-                const uint32_t pixel = rp.pixel_list ? rp.pixel_list[li] : li;
-                const uint32_t sample = rp.first_sample + k;
-                const int px = int(pixel % uint32_t(rp.width)), py = int(pixel / uint32_t(rp.width));
-                Philox g;
-                g.init(rp.seed, rp.stream, pixel, sample, 0, 0);
-                // engine.h:62-63 — row 0 is the top of the image, v is flipped
-                const double u = (px + g.next_double()) / (rp.width - 1);
-                const double v = ((rp.height - 1 - py) + g.next_double()) / (rp.height - 1);
-                const DRay r = camera_ray(rp.cam, u, v, g);
-                store_ray(w.rays, slot, r);
-                PathAux a;
-                a.thr[0] = a.thr[1] = a.thr[2] = 1.f;
-                a.pixel = pixel; a.sample = sample; a.rng_block = g.c2; a.depth = 0; a.pad = 0;
-                *reinterpret_cast<uint4*>(w.aux + slot) = *reinterpret_cast<const uint4*>(&a);
-                *(reinterpret_cast<uint4*>(w.aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
-            }
-        }
-        queue_push(w.q_extend[cur], &c->n_extend[cur], spawned, slot, lane);
-        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], valid && !spawned, slot, lane);
-    }
-}
-
-__global__ void k_after_generate(WaveCounters* c, int cur)
-{
-    const unsigned long long left = c->total - c->issued;
-    const unsigned long long n = c->n_regen[cur];
-    c->issued += n < left ? n : left;
-    c->n_regen[cur] = 0;
-    c->cursor = 0;
-}
-
-#ifndef ARTB_EXTEND_MIN_BLOCKS
-#define ARTB_EXTEND_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, ARTB_EXTEND_MIN_BLOCKS) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+// Closest hit for every ray of q_extend[cur]. Misses add the background and hand their slot to the free list;
+// hits are binned by the material type of the primitive they landed on.
+__global__ void __launch_bounds__(128, 4) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
 {
     WaveCounters* c = w.c;
     const uint32_t n = c->n_extend[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
+        const unsigned long long left = c->total - c->issued;
+        const unsigned long long nr = c->n_out[cur ^ 1][Q_REGEN];
+        c->issued += nr < left ? nr : left;
+        c->n_out[cur ^ 1][Q_REGEN] = 0;
+        c->rays += n;
+    }
     const int lane = threadIdx.x & 31;
     while (true) {
         uint32_t base = 0;
@@ -198,11 +189,9 @@ __global__ void __launch_bounds__(128, ARTB_EXTEND_MIN_BLOCKS) k_extend(WaveBuff
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const uint32_t i = base + lane;
-        const bool valid = i < n;
         uint32_t slot = 0;
-        int mat = -1;
-        bool miss = false;
-        if (valid) {
+        int key = -1;
+        if (i < n) {
             slot = w.q_extend[cur][i];
             const DRay r = load_ray(w.rays, slot);
             const PathAux* a = w.aux + slot;
@@ -211,47 +200,86 @@ __global__ void __launch_bounds__(128, ARTB_EXTEND_MIN_BLOCKS) k_extend(WaveBuff
             xi.path_lo = a->pixel; xi.path_hi = a->sample; xi.bounce = a->depth;
             const ClosestHit h = closest_hit(s, r, 0.001, INFINITY, xi);
             if (h.prim < 0) {
-                miss = true;
+                key = Q_REGEN;
                 add_radiance(rp, a->pixel, a->thr[0] * float(s.background[0]), a->thr[1] * float(s.background[1]),
                              a->thr[2] * float(s.background[2]));
             } else {
                 PathHit ph; ph.t = h.t; ph.prim = h.prim; ph.pad = 0;
                 *reinterpret_cast<double2*>(w.hits + slot) = *reinterpret_cast<const double2*>(&ph);
-                mat = int(s.materials[s.prims[h.prim].material].type);
+                key = int(s.materials[s.prims[h.prim].material].type);
             }
         }
-        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], miss, slot, lane);
-#pragma unroll
-        for (int m = 0; m < MAT_COUNT; ++m) queue_push(w.q_shade[m], &c->n_shade[m], mat == m, slot, lane);
+        const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
+        if (key >= 0) {
+            uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
+            q[pos] = slot;
+        }
     }
 }
 
+// One warp = 32 entries of ONE queue: the hits of one material type (hit record, texture, emitted, scatter), or 32
+// free slots that start the next (pixel, sample) of the round: _stochastic_sample (engine.h:62-63) + camera::get_ray.
+// Scattered and fresh rays go to q_extend[cur^1]; slots whose path ended (light, absorbed, depth limit) or that found
+// no sample left go to the free list q_regen[cur^1].
 __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, RoundParams rp, int cur)
 {
     WaveCounters* c = w.c;
-    uint32_t start[MAT_COUNT + 1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        c->n_extend[cur] = 0;
+#pragma unroll
+        for (int m = 0; m < MAT_COUNT; ++m) c->n_out[cur ^ 1][m] = 0;
+        c->cursor = 0;
+    }
+    uint32_t start[Q_OUT_COUNT + 1];
     start[0] = 0;
 #pragma unroll
-    for (int m = 0; m < MAT_COUNT; ++m) start[m + 1] = start[m] + ((c->n_shade[m] + 31u) >> 5);
+    for (int m = 0; m < Q_OUT_COUNT; ++m) start[m + 1] = start[m] + ((c->n_out[cur][m] + 31u) >> 5);
+    const unsigned long long issued = c->issued, total = c->total;
+    const uint32_t n_list = c->n_list;
     const int lane = threadIdx.x & 31;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < start[MAT_COUNT]; wi += n_warps) {
+    for (uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < start[Q_OUT_COUNT]; wi += n_warps) {
         int m = 0;
 #pragma unroll
-        for (int k = 1; k < MAT_COUNT; ++k) if (wi >= start[k]) m = k;
+        for (int k = 1; k < Q_OUT_COUNT; ++k) if (wi >= start[k]) m = k;
         const uint32_t i = (wi - start[m]) * 32u + uint32_t(lane);
-        const bool valid = i < c->n_shade[m];
+        const bool valid = i < c->n_out[cur][m];
         uint32_t slot = 0;
-        bool cont = false;
-        if (valid) {
-            slot = w.q_shade[m][i];
+        int key = -1;                       // 0: a ray for the next wave, 1: slot is free
+        if (m == Q_REGEN) {
+            if (valid) {
+                slot = w.q_regen[cur][i];
+                const unsigned long long sidx = issued + i;
+                key = 1;
+                if (sidx < total) {
+                    key = 0;
+                    const uint32_t li = uint32_t(sidx % n_list);
+                    const uint32_t k = uint32_t(sidx / n_list);
+                    const uint32_t pixel = rp.pixel_list ? rp.pixel_list[li] : li;
+                    const uint32_t sample = rp.first_sample + k;
+                    const int px = int(pixel % uint32_t(rp.width)), py = int(pixel / uint32_t(rp.width));
+                    Philox g;
+                    g.init(rp.seed, rp.stream, pixel, sample, 0, 0);
+                    // engine.h:62-63 — row 0 is the top of the image, v is flipped
+                    const double u = (px + g.next_double()) / (rp.width - 1);
+                    const double v = ((rp.height - 1 - py) + g.next_double()) / (rp.height - 1);
+                    const DRay r = camera_ray(rp.cam, u, v, g);
+                    store_ray(w.rays, slot, r);
+                    PathAux a;
+                    a.thr[0] = a.thr[1] = a.thr[2] = 1.f;
+                    a.pixel = pixel; a.sample = sample; a.rng_block = g.c2; a.depth = 0; a.pad = 0;
+                    store_aux(w.aux, slot, a);
+                }
+            }
+        } else if (valid) {
+            slot = w.q_shade[size_t(m) * w.pool + i];
             const DRay r = load_ray(w.rays, slot);
             PathAux a;
-            *reinterpret_cast<uint4*>(&a) = *reinterpret_cast<const uint4*>(w.aux + slot);
-            *(reinterpret_cast<uint4*>(&a) + 1) = *(reinterpret_cast<const uint4*>(w.aux + slot) + 1);
+            load_aux(w.aux, slot, a);
             const PathHit ph = w.hits[slot];
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
+            key = 1;
             if (mat.type == MAT_DIFFUSE_LIGHT) {
                 const d3 e = material_emitted(s, mat, h);
                 add_radiance(rp, a.pixel, a.thr[0] * float(e.x), a.thr[1] * float(e.y), a.thr[2] * float(e.z));
@@ -261,28 +289,19 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
                 d3 att; DRay sc;
                 const bool ok = material_scatter(s, mat, r, h, g, att, sc);
                 if (ok && a.depth + 1u < uint32_t(rp.max_depth)) {
-                    cont = true;
+                    key = 0;
                     store_ray(w.rays, slot, sc);
                     a.thr[0] *= float(att.x); a.thr[1] *= float(att.y); a.thr[2] *= float(att.z);
                     a.depth += 1; a.rng_block = g.c2;
-                    *reinterpret_cast<uint4*>(w.aux + slot) = *reinterpret_cast<const uint4*>(&a);
-                    *(reinterpret_cast<uint4*>(w.aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
+                    store_aux(w.aux, slot, a);
                 } else {
                     add_radiance(rp, a.pixel, 0.f, 0.f, 0.f);   // absorbed / depth limit: a black sample (engine.h:451-452, 462-463)
                 }
             }
         }
-        queue_push(w.q_extend[cur ^ 1], &c->n_extend[cur ^ 1], cont, slot, lane);
-        queue_push(w.q_regen[cur ^ 1], &c->n_regen[cur ^ 1], valid && !cont, slot, lane);
+        const uint32_t pos = multi_queue_reserve(key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1], lane);
+        if (key >= 0) (key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1])[pos] = slot;
     }
-}
-
-__global__ void k_after_shade(WaveCounters* c, int cur)
-{
-    c->rays += c->n_extend[cur];
-    c->n_extend[cur] = 0;
-    for (int m = 0; m < MAT_COUNT; ++m) c->n_shade[m] = 0;
-
 }
 
 // adaptive variance mask: keep the pixels of the current list whose luminance mean is not yet settled.
@@ -437,7 +456,7 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
         w.q_extend[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
         w.q_regen[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
     }
-    for (int m = 0; m < MAT_COUNT; ++m) w.q_shade[m] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
+    w.q_shade = dev_alloc<uint32_t>(impl_->pool_allocs, size_t(pool_paths) * MAT_COUNT);
     w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
     CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
 }
@@ -486,6 +505,7 @@ void Renderer::upload(const FlatScene& fs)
     v.n_materials = uint32_t(fs.materials.size());
     v.n_textures = uint32_t(fs.textures.size());
     v.n_global_prims = fs.n_global_prims;
+    v.n_global_media = fs.n_global_media;
     v.root = fs.root;
     for (int k = 0; k < 3; ++k) v.background[k] = fs.background[k];
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -605,7 +625,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     rp.count = p.adaptive ? count_dev : nullptr;
     rp.lumsq = p.adaptive ? I.lumsq : nullptr;
 
-    const int gen_blocks = I.sm_count * 4, ext_blocks = I.sm_count * 8, shade_blocks = I.sm_count * 8;
+    const int ext_blocks = I.sm_count * 8, shade_blocks = I.sm_count * 8;
     RenderStats S;
     cudaEvent_t ev_begin, ev_end;
     CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
@@ -631,6 +651,8 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     k_init_pool<<<(w.pool + 255) / 256, 256, 0, st>>>(w);
     S.launches++;
 
+    // One wave = k_shade(cur) [shade the hits of the previous wave + start new paths in free slots] followed by
+    // k_extend(cur^1) [closest hits of everything k_shade queued]. The host only looks at the counters every few waves.
     int cur = 0;
     auto run_round = [&](long long n_list_fixed, const uint32_t* list, uint32_t first_sample, uint32_t batch) {
         rp.pixel_list = list;
@@ -641,25 +663,24 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
         int check_every = 4;
         while (true) {
             for (int k = 0; k < check_every; ++k) {
-                k_generate<<<gen_blocks, 256, 0, st>>>(w, rp, cur);
-                k_after_generate<<<1, 1, 0, st>>>(w.c, cur);
+                k_shade<<<shade_blocks, 128, 0, st>>>(w, view_, rp, cur);
+                cur ^= 1;
                 if (profile) {
                     if (pairs_used == kPairs) drain();
                     CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used], st));
                 }
                 k_extend<<<ext_blocks, 128, 0, st>>>(w, view_, rp, cur);
                 if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used + 1], st)); pairs_used++; }
-                k_shade<<<shade_blocks, 128, 0, st>>>(w, view_, rp, cur);
-                k_after_shade<<<1, 1, 0, st>>>(w.c, cur);
-                cur ^= 1;
-                S.launches += 5;
+                S.launches += 2;
                 S.waves++;
             }
             CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
             CUDA_CHECK(cudaGetLastError());
             const WaveCounters& c = *I.counters_host;
-            if (c.issued >= c.total && c.n_extend[cur] == 0) break;
+            uint32_t pending = 0;
+            for (int m = 0; m < MAT_COUNT; ++m) pending += c.n_out[cur][m];
+            if (c.issued >= c.total && pending == 0) break;
             if (check_every < 32) check_every *= 2;
         }
     };

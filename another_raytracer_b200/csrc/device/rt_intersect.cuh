@@ -151,14 +151,50 @@ struct MediumXi {
     }
 };
 
-__device__ inline bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
-                                const MediumXi& xi, double& t)
+// The two boundary queries of a medium (constant_medium.h:44-47): rec1 = boundary.hit(-inf, inf),
+// rec2 = boundary.hit(rec1.t + 0.0001, inf).
+__device__ __noinline__ bool medium_interval_general(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                                                     double& t1, double& t2)
+{
+    if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, t1)) return false;
+    return boundary_t(s, first, count, world, t1 + 0.0001, INFINITY, t2);
+}
+
+__device__ __forceinline__ bool medium_interval(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                                                double& t1, double& t2)
+{
+    const FlatPrim& b = s.prims[first];
+    if (count == 1 && b.type == PRIM_SPHERE) {
+        // One sphere: both queries evaluate the same two roots (sphere.h:40-57), so compute them once. The first
+        // query has no bounds and returns the smaller root; the second one rejects it (it is below its t_min) and
+        // accepts the larger root iff that is >= t_min. Same expressions, hence the same numbers as two calls.
+        const DRay r = to_object_space(s, b.xform, world);
+        const d3 oc = r.o - ld3(b.g);
+        const double a = length_squared(r.d);
+        const double half_b = dot(oc, r.d);
+        const double c = length_squared(oc) - b.g[3] * b.g[3];
+        const double discriminant = half_b * half_b - a * c;
+        if (discriminant < 0) return false;
+        const double sqrtd = sqrt(discriminant);
+        const double r1 = (-half_b - sqrtd) / a;
+        const double r2 = (-half_b + sqrtd) / a;
+        const double t_min2 = r1 + 0.0001;
+        if (r1 < t_min2 && fabs(r1) <= DBL_MAX) {      // always, except for degenerate rays: those take the general path
+            if (r2 < t_min2) return false;
+            t1 = r1; t2 = r2;
+            return true;
+        }
+    }
+    return medium_interval_general(s, first, count, world, t1, t2);
+}
+
+__device__ __forceinline__ bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
+                                         const MediumXi& xi, double& t)
 {
     // constant_medium.h:44-69
     const uint32_t first = uint32_t(p.g[1]), count = uint32_t(p.g[2]);
     double t1, t2;
-    if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, t1)) return false;
-    if (!boundary_t(s, first, count, world, t1 + 0.0001, INFINITY, t2)) return false;
+    if (!medium_interval(s, first, count, world, t1, t2)) return false;
     if (t1 < t_min) t1 = t_min;
     if (t2 > t_max) t2 = t_max;
     if (t1 >= t2) return false;
@@ -169,6 +205,13 @@ __device__ inline bool medium_t(const SceneView& s, const FlatPrim& p, const DRa
     // explicit-xi table: NaN marks "the reference drew nothing here", i.e. its interval was already empty
     // because a closer surface had been found first — then this medium cannot be the closest hit either
     if (!(u == u)) return false;
+    // Most queries end here with "scattered beyond the interval". Decide the clear cases with a float logarithm:
+    // |log(u) - __logf(float(u))| <= 1e-6 (1 + |log u|) (2^-21.4 absolute / 3 ulp, plus the rounding of u), so a
+    // lower bound of hit_distance that already exceeds the interval is a certain miss; everything else takes the
+    // reference's double-precision expression below.
+    const float lf = __logf(float(u));
+    const double hit_distance_lo = -p.g[0] * double(-lf - 1e-6f * (1.f - lf));
+    if (hit_distance_lo > distance_inside_boundary) return false;
     const double hit_distance = p.g[0] * log(u);
     if (hit_distance > distance_inside_boundary) return false;
     t = t1 + hit_distance / ray_length;
@@ -178,21 +221,16 @@ __device__ inline bool medium_t(const SceneView& s, const FlatPrim& p, const DRa
 // ---- BVH traversal ------------------------------------------------------------------------------
 struct ClosestHit { double t; int32_t prim; uint32_t dfs; };
 
+// surfaces of one leaf (or of the global list); media never sit in leaves (flatten.cpp: they are all global)
 __device__ __forceinline__ void test_prims(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                           double t_min, const MediumXi& xi, ClosestHit& best,
-                                           uint32_t& cached_xform, DRay& cached_ray)
+                                           double t_min, ClosestHit& best, uint32_t& cached_xform, DRay& cached_ray)
 {
     for (uint32_t i = first; i < first + count; ++i) {
         const FlatPrim& p = s.prims[i];
+        if (p.type == PRIM_MEDIUM) continue;
+        if (p.xform != cached_xform) { cached_ray = to_object_space(s, p.xform, world); cached_xform = p.xform; }
         double t;
-        bool ok;
-        if (p.type == PRIM_MEDIUM) {
-            ok = medium_t(s, p, world, t_min, best.t, xi, t);
-        } else {
-            if (p.xform != cached_xform) { cached_ray = to_object_space(s, p.xform, world); cached_xform = p.xform; }
-            ok = surface_t(p, cached_ray, t_min, best.t, t);
-        }
-        if (ok && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
+        if (surface_t(p, cached_ray, t_min, best.t, t) && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
             best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
         }
     }
@@ -250,21 +288,10 @@ __device__ __forceinline__ bool slab(const float* lo, const float* hi, const Sla
 // "while-while" traversal (Aila & Laine 2009): an inner loop that only walks internal nodes until this lane holds
 // a leaf, then an inner loop that only intersects primitives. The lanes of a warp re-converge between the two, so
 // node tests run next to node tests and primitive tests next to primitive tests.
-__device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi)
+__device__ __forceinline__ void traverse_bvh(const SceneView& s, const DRay& ray, const SlabRay& sr, double t_min, float t_min_f,
+                                             ClosestHit& best, uint32_t& cached_xform, DRay& cached_ray)
 {
-    ClosestHit best;
-    best.t = t_max; best.prim = -1; best.dfs = 0;
-    uint32_t cached_xform = 0;
-    DRay cached_ray = ray;
-
-    // global primitives first: same work for every lane, and an early t_max for the traversal
-    if (s.n_global_prims) test_prims(s, 0, s.n_global_prims, ray, t_min, xi, best, cached_xform, cached_ray);
-    if (s.n_world_prims == s.n_global_prims) return best;
-
-    const SlabRay sr = make_slab_ray(ray);
-    const float t_min_f = __double2float_rd(t_min);
     float t_best_f = __double2float_ru(best.t);
-
     int32_t stack[ARTB_STACK_DEPTH];
     int sp = 0;
     int32_t cur = s.root;            // >= 0 internal node, < 0 leaf code
@@ -291,9 +318,38 @@ __device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, do
         // ---- intersect the leaf
         if (cur != kDone) {
             const uint32_t code = uint32_t(~cur);
-            test_prims(s, code >> 3, (code & 7u) + 1u, ray, t_min, xi, best, cached_xform, cached_ray);
+            test_prims(s, code >> 3, (code & 7u) + 1u, ray, t_min, best, cached_xform, cached_ray);
             t_best_f = __double2float_ru(best.t);
             cur = sp ? stack[--sp] : kDone;
+        }
+    }
+}
+
+__device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi)
+{
+    ClosestHit best;
+    best.t = t_max; best.prim = -1; best.dfs = 0;
+    uint32_t cached_xform = 0;
+    DRay cached_ray = ray;
+
+    const uint32_t n_surf = s.n_global_prims - s.n_global_media;
+    const SlabRay sr = make_slab_ray(ray);
+    const float t_min_f = __double2float_rd(t_min);
+    // global surfaces first: same work for every lane, and an early t_max for the traversal
+    if (n_surf) test_prims(s, 0, n_surf, ray, t_min, best, cached_xform, cached_ray);
+    if (s.n_world_prims > s.n_global_prims) traverse_bvh(s, ray, sr, t_min, t_min_f, best, cached_xform, cached_ray);
+    // Media last: their candidate t does not depend on the order either, but with the final t_max the
+    // interval is short, a medium whose box starts beyond the closest surface is skipped after six FMAs, and most of
+    // the others leave through the float-logarithm exit of medium_t.
+    for (uint32_t i = n_surf; i < s.n_global_prims; ++i) {
+        const FlatPrim& p = s.prims[i];
+        const float lo[3] = { __double2float_rd(p.g[4]), __double2float_rd(p.g[5]), __double2float_rd(p.g[6]) };
+        const float hi[3] = { __double2float_ru(p.g[7]), __double2float_ru(p.g[8]), __double2float_ru(p.g[9]) };
+        float enter;
+        if (!slab(lo, hi, sr, t_min_f, __double2float_ru(best.t), enter)) continue;
+        double t;
+        if (medium_t(s, p, ray, t_min, best.t, xi, t) && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
+            best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
         }
     }
     return best;

@@ -459,8 +459,18 @@ private:
 
     void build_bvh()
     {
-        // 1. global primitives: boxes that span a large share of the scene are pulled out of the tree
-        std::vector<Item> globals, rest = world_items;
+        // 1. global primitives, tested for every ray outside the tree: every constant_medium (its test is two boundary
+        //    queries + a random draw: the device runs it once per ray, AFTER the traversal, when the final t_max makes
+        //    the interval short; g[4..9] keep the medium's world box for a cheap pre-test), and surfaces whose boxes span
+        //    a large share of the scene (no divergence, and an early t_max for the traversal)
+        std::vector<Item> globals, media, rest;
+        for (const Item& it : world_items) {
+            if (it.prim.type == PRIM_MEDIUM) {
+                Item m = it;
+                for (int k = 0; k < 3; ++k) { m.prim.g[4 + k] = it.box.lo[k]; m.prim.g[7 + k] = it.box.hi[k]; }
+                media.push_back(m);
+            } else rest.push_back(it);
+        }
         for (int pass = 0; pass < 4 && int(globals.size()) < opt.max_global_prims; ++pass) {
             Box3 all;
             for (const Item& it : rest) all.grow(it.box);
@@ -475,14 +485,20 @@ private:
             rest.swap(keep);
             if (!moved) break;
         }
-        if (world_items.size() <= size_t(opt.max_global_prims)) { globals = world_items; rest.clear(); }   // tiny scene: a plain list
+        if (rest.size() + globals.size() <= size_t(opt.max_global_prims)) {   // tiny scene: a plain list
+            globals.insert(globals.end(), rest.begin(), rest.end());
+            rest.clear();
+        }
+        // globals keep the reference's test order (dfs), which makes early best-t pruning deterministic; media last
+        std::sort(globals.begin(), globals.end(), [](const Item& a, const Item& b) { return a.prim.dfs_id < b.prim.dfs_id; });
+        std::sort(media.begin(), media.end(), [](const Item& a, const Item& b) { return a.prim.dfs_id < b.prim.dfs_id; });
+        out.n_global_media = uint32_t(media.size());
+        globals.insert(globals.end(), media.begin(), media.end());
         out.n_global_prims = uint32_t(globals.size());
         out.n_world_prims = uint32_t(world_items.size());
         Box3 whole;
         for (const Item& it : world_items) whole.grow(it.box);
         for (int k = 0; k < 3; ++k) { out.world_lo[k] = whole.valid() ? whole.lo[k] : 0; out.world_hi[k] = whole.valid() ? whole.hi[k] : 0; }
-        // globals keep the reference's test order (dfs), which makes early best-t pruning deterministic
-        std::sort(globals.begin(), globals.end(), [](const Item& a, const Item& b) { return a.prim.dfs_id < b.prim.dfs_id; });
         out.prims.reserve(world_items.size() + boundary_items.size());
         for (const Item& it : globals) out.prims.push_back(it.prim);
 

@@ -37,6 +37,7 @@ struct FlatScene {
     std::vector<FlatPerlin> perlins;
     uint32_t n_world_prims = 0;
     uint32_t n_global_prims = 0;
+    uint32_t n_global_media = 0;          // the last n_global_media globals are the scene's constant_media
     uint32_t n_media = 0;
     uint32_t n_leaves_total = 0;          // dfs ids handed out (reachable or not)
     uint32_t n_culled = 0;
