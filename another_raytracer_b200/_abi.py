@@ -49,7 +49,7 @@ class SceneInfo(C.Structure):
 
 class FlatSceneView(C.Structure):
     _fields_ = [("prims", C.c_void_p), ("n_prims", C.c_uint32), ("n_world_prims", C.c_uint32),
-                ("nodes", C.c_void_p), ("n_nodes", C.c_uint32), ("root", C.c_int32), ("n_global_prims", C.c_uint32),
+                ("nodes", C.c_void_p), ("n_nodes", C.c_uint32), ("reserved0", C.c_int32), ("n_global_prims", C.c_uint32),
                 ("bvh_depth", C.c_int32),
                 ("xform_ops", C.c_void_p), ("n_xform_ops", C.c_uint32),
                 ("xforms", C.c_void_p), ("n_xforms", C.c_uint32),

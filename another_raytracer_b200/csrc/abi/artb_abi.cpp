@@ -31,7 +31,7 @@ struct artb_ctx {
 };
 
 static_assert(sizeof(artb_hit) == sizeof(HitRecordOut), "artb_hit must match the device record");
-static_assert(sizeof(FlatPrim) == 96 && sizeof(FlatNode) == 64 && sizeof(FlatXformOp) == 32 && sizeof(FlatXform) == 8 &&
+static_assert(sizeof(FlatPrim) == 96 && sizeof(FlatNode8) == 80 && sizeof(FlatXformOp) == 32 && sizeof(FlatXform) == 8 &&
               sizeof(FlatMaterial) == 48 && sizeof(FlatTexture) == 96 && sizeof(FlatImage) == 24 && sizeof(FlatPerlin) == 9216,
               "flat record sizes are part of the ABI");
 
@@ -189,7 +189,7 @@ int artb_scene_get_info(const artb_scene* s, artb_scene_info* out)
     out->n_images = uint32_t(f.images.size()); out->n_xforms = uint32_t(f.xforms.size());
     out->n_leaves_total = f.n_leaves_total; out->n_culled = f.n_culled; out->bvh_depth = uint32_t(f.bvh_depth);
     out->top_level_objects = uint32_t(s->host.objects.objects.size());
-    out->flat_bytes = f.prims.size() * sizeof(FlatPrim) + f.nodes.size() * sizeof(FlatNode) + f.xform_ops.size() * sizeof(FlatXformOp) +
+    out->flat_bytes = f.prims.size() * sizeof(FlatPrim) + f.nodes.size() * sizeof(FlatNode8) + f.xform_ops.size() * sizeof(FlatXformOp) +
                       f.xforms.size() * sizeof(FlatXform) + f.materials.size() * sizeof(FlatMaterial) +
                       f.textures.size() * sizeof(FlatTexture) + f.images.size() * sizeof(FlatImage) + f.texels.size() +
                       f.perlins.size() * sizeof(FlatPerlin);
@@ -216,7 +216,7 @@ int artb_scene_get_flat(const artb_scene* s, artb_flat_scene* out)
     std::memset(out, 0, sizeof(*out));
     out->prims = f.prims.data(); out->n_prims = uint32_t(f.prims.size()); out->n_world_prims = f.n_world_prims;
     out->nodes = f.nodes.data(); out->n_nodes = uint32_t(f.nodes.size());
-    out->root = f.root; out->n_global_prims = f.n_global_prims; out->bvh_depth = f.bvh_depth;
+    out->reserved0 = 0; out->n_global_prims = f.n_global_prims; out->bvh_depth = f.bvh_depth;
     out->xform_ops = f.xform_ops.data(); out->n_xform_ops = uint32_t(f.xform_ops.size());
     out->xforms = f.xforms.data(); out->n_xforms = uint32_t(f.xforms.size());
     out->materials = f.materials.data(); out->n_materials = uint32_t(f.materials.size());
@@ -263,7 +263,7 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
         copy(fs.texels, f->texels, f->n_texel_bytes);
         copy(fs.perlins, f->perlins, f->n_perlins);
         fs.n_world_prims = f->n_world_prims; fs.n_media = f->n_media;
-        fs.root = f->root; fs.n_global_prims = f->n_global_prims; fs.bvh_depth = f->bvh_depth;
+        fs.n_global_prims = f->n_global_prims; fs.bvh_depth = f->bvh_depth;
         // every constant_medium must sit at the END of the global range (the device tests media after the traversal)
         for (uint32_t i = 0; i < fs.n_world_prims; ++i) {
             const bool is_medium = fs.prims[i].type == PRIM_MEDIUM;
@@ -279,14 +279,28 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
             if (p.type == PRIM_MEDIUM && (p.g[1] < fs.n_world_prims || p.g[1] + p.g[2] > double(fs.prims.size())))
                 throw std::logic_error("flat scene: medium boundary range out of bounds");
         }
-        auto check_ref = [&](int32_t ref) {
-            if (ref >= 0) { if (size_t(ref) >= fs.nodes.size()) throw std::logic_error("flat scene: BVH child out of bounds"); return; }
-            const uint32_t code = uint32_t(~ref), first = code >> 3, count = (code & 7u) + 1u;
-            if (first < fs.n_global_prims || size_t(first) + count > fs.n_world_prims)
-                throw std::logic_error("flat scene: BVH leaf out of bounds");
-        };
-        if (fs.n_world_prims > fs.n_global_prims) check_ref(fs.root);
-        for (const FlatNode& n : fs.nodes) { check_ref(n.child0); check_ref(n.child1); }
+        if (fs.n_world_prims > fs.n_global_prims && fs.nodes.empty()) throw std::logic_error("flat scene: BVH primitives without nodes");
+        if (fs.bvh_depth < 0 || fs.bvh_depth > 24) throw std::logic_error("flat scene: bvh_depth out of range");
+        for (const FlatNode8& n : fs.nodes) {
+            uint32_t inner = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                const uint32_t m = n.meta[sl];
+                if (m == 0) { if (n.imask & (1u << sl)) throw std::logic_error("flat scene: imask marks an empty slot"); continue; }
+                if ((m & 0x18u) == 0x18u) {          // 24 + slot: internal child
+                    if (m != ((1u << 5) | (24u + uint32_t(sl))) || !(n.imask & (1u << sl))) throw std::logic_error("flat scene: bad internal child");
+                    ++inner;
+                } else {
+                    const uint32_t bits = m >> 5, off = m & 31u;
+                    const uint32_t count = bits == 1 ? 1 : bits == 3 ? 2 : bits == 7 ? 3 : 0;
+                    if (!count || (n.imask & (1u << sl)) || off + count > 24 || n.prim_base < fs.n_global_prims ||
+                        size_t(n.prim_base) + off + count > fs.n_world_prims)
+                        throw std::logic_error("flat scene: BVH leaf out of bounds");
+                }
+                for (int a = 0; a < 3; ++a)
+                    if (n.e[a] < 1 || n.e[a] > 254) throw std::logic_error("flat scene: bad quantisation exponent");
+            }
+            if (inner && size_t(n.child_base) + inner > fs.nodes.size()) throw std::logic_error("flat scene: BVH child out of bounds");
+        }
         for (const FlatXform& x : fs.xforms)
             if (size_t(x.first_op) + x.n_ops > fs.xform_ops.size() || x.n_ops > 8) throw std::logic_error("flat scene: bad transform chain");
         for (const FlatMaterial& m : fs.materials)

@@ -6,7 +6,7 @@
 //   prims[]      one fixed-size record per leaf primitive: first the few "global" primitives whose box spans a
 //                large part of the scene (tested for every ray before the traversal: no divergence, and an
 //                early t_max), then the BVH leaves in leaf order, then the media boundaries
-//   nodes[]      one binary BVH over ALL world primitives in WORLD space (instanced primitives keep their
+//   nodes[]      one 8-wide BVH over ALL world primitives in WORLD space (instanced primitives keep their
 //                object-space geometry and a transform-chain id; their world boxes bound the transformed
 //                geometry). The closest hit does not depend on the acceleration structure, so this
 //                single tree replaces the reference's list-of-BVHs-of-instances and is bit-compatible
@@ -45,20 +45,30 @@ struct ARTB_ALIGN(16) FlatPrim {      // 96 B
     uint32_t dfs_id;      // position in the reference's depth-first test order: reported id + tie-break
 };
 
-// Binary BVH node holding BOTH children's boxes, so one 64-byte fetch (four 16-byte loads) decides both
-// descents. Boxes are FLOAT, rounded OUTWARD from the double-precision world boxes: the node test only has
-// to be conservative (it may admit a ray that misses, never reject one that hits), because every candidate
-// primitive is re-tested with the reference's double-precision formula. FP32 slabs issue at twice the FP64
-// rate, need no multi-instruction double min/max, and halve the node bytes.
-// child >= 0: internal node index. child < 0: leaf, code = ~child = (first_prim << 3) | (count - 1).
-struct ARTB_ALIGN(16) FlatNode {      // 64 B
-    float lo0[3], hi0[3];
-    float lo1[3], hi1[3];
-    int32_t child0, child1;
-    int32_t pad[2];
+// 8-wide BVH node with boxes quantised to 8 bits per plane on a per-node grid (the compressed wide BVH of Ylitie,
+// Karras & Laine, HPG 2017): 80 bytes = five 16-byte loads decide up to eight descents, and the whole tree of the
+// reference's scenes (a few hundred nodes) fits in one SM's shared memory, where k_extend stages it.
+//   child box plane (axis a)  =  p[a] + q * 2^(e[a]-127),  q in 0..255; lo planes rounded DOWN, hi planes UP, so the
+//   quantised box CONTAINS the double-precision world box. The node test only has to be conservative (it may admit
+//   a ray that misses, never reject one that hits): every candidate primitive is re-tested with the reference's
+//   double-precision formula, so results do not depend on the tree at all — only the amount of work does.
+//   slot s (0..7): meta[s] = 0                          empty
+//                  meta[s] = 0b001'00000 | (24 + s)     internal child; its node index is child_base + (number of
+//                                                       internal slots below s), imask has bit s set
+//                  meta[s] = unary(count) << 5 | offset  leaf of `count` (1..3) primitives prims[prim_base + offset ..]
+//   Children are placed in slots so that a ray of octant o (bit 2: dx<0, bit 1: dy<0, bit 0: dz<0) meets them roughly
+//   front to back when it visits slots in the order of decreasing (slot XOR (7-o)).
+struct ARTB_ALIGN(16) FlatNode8 {     // 80 B
+    float p[3];
+    uint8_t e[3];
+    uint8_t imask;
+    uint32_t child_base;
+    uint32_t prim_base;
+    uint8_t meta[8];
+    uint8_t qlo[3][8];
+    uint8_t qhi[3][8];
 };
-#define ARTB_MAX_LEAF_PRIMS 8
-#define ARTB_LEAF_CODE(first, count) (~int32_t((uint32_t(first) << 3) | uint32_t((count) - 1)))
+#define ARTB_MAX_LEAF_PRIMS 3
 
 enum : uint32_t { XFORM_TRANSLATE = 0, XFORM_ROTATE_Y = 1 };
 
@@ -101,7 +111,7 @@ struct FlatPerlin {       // perlin.h:56-61
 // device-side view (all pointers are device pointers)
 struct SceneView {
     const FlatPrim* prims;
-    const FlatNode* nodes;
+    const FlatNode8* nodes;
     const FlatXformOp* xform_ops;
     const FlatXform* xforms;
     const FlatMaterial* materials;
@@ -111,7 +121,6 @@ struct SceneView {
     const FlatPerlin* perlins;
     uint32_t n_prims, n_world_prims, n_global_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
     uint32_t n_global_media;          // media among the global primitives (tested after the traversal)
-    int32_t root;                     // root child reference (internal index or leaf code); valid if n_world_prims > n_global_prims
     double background[3];
 };
 

@@ -18,6 +18,7 @@
 #include "rt_shade.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <vector>
 
@@ -170,7 +171,19 @@ __global__ void k_round_begin(WaveCounters* c, long long n_list_fixed, uint32_t 
 
 // Closest hit for every ray of q_extend[cur]. Misses add the background and hand their slot to the free list;
 // hits are binned by the material type of the primitive they landed on.
-__global__ void __launch_bounds__(128, 4) k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+// kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
+// scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
+// Otherwise (trees beyond the shared-memory budget) nodes are read through L1/L2.
+// (Per-lane refill of finished rays was tried and lost: every stop of the warp to finish / refill a few lanes costs
+// more round trips than the idle lanes it saves; see DESIGN.md.)
+#ifndef ARTB_EXTEND_THREADS
+#define ARTB_EXTEND_THREADS 512
+#endif
+extern __shared__ uint4 smem_nodes[];
+
+template <bool kShared>
+__global__ void __launch_bounds__(kShared ? ARTB_EXTEND_THREADS : 128, kShared ? 1 : 4)
+k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
 {
     WaveCounters* c = w.c;
     const uint32_t n = c->n_extend[cur];
@@ -182,38 +195,61 @@ __global__ void __launch_bounds__(128, 4) k_extend(WaveBuffers w, SceneView s, R
         c->n_out[cur ^ 1][Q_REGEN] = 0;
         c->rays += n;
     }
+    if (n == 0) return;
+    const FlatNode8* nodes = s.nodes;
+    if (kShared) {
+        const uint4* src = reinterpret_cast<const uint4*>(s.nodes);
+        for (uint32_t i = threadIdx.x; i < s.n_nodes * 5u; i += blockDim.x) smem_nodes[i] = __ldg(src + i);
+        __syncthreads();
+        nodes = reinterpret_cast<const FlatNode8*>(smem_nodes);
+    }
     const int lane = threadIdx.x & 31;
-    while (true) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&c->cursor, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        uint32_t slot = 0;
+    // Chunks of 32 rays are handed out by an atomic cursor. The grab for the NEXT chunk and the load of its slot ids
+    // are issued before the current chunk is traversed, and its ray records are prefetched before the current
+    // chunk's queue appends, so none of those round trips is waited for.
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&c->cursor, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    uint32_t slot = base + lane < n ? w.q_extend[cur][base + lane] : 0u;
+    while (base < n) {
+        const bool valid = base + lane < n;
+        uint32_t next_base = 0;
+        if (lane == 0) next_base = atomicAdd(&c->cursor, 32u);
         int key = -1;
-        if (i < n) {
-            slot = w.q_extend[cur][i];
-            const DRay r = load_ray(w.rays, slot);
-            const PathAux* a = w.aux + slot;
+        DRay r;
+        PathAux a;
+        if (valid) {
+            r = load_ray(w.rays, slot);
+            load_aux(w.aux, slot, a);
+        }
+        next_base = __shfl_sync(0xffffffffu, next_base, 0);
+        const uint32_t next_slot = next_base + lane < n ? w.q_extend[cur][next_base + lane] : 0u;
+        if (valid) {
             MediumXi xi;
             xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
-            xi.path_lo = a->pixel; xi.path_hi = a->sample; xi.bounce = a->depth;
-            const ClosestHit h = closest_hit(s, r, 0.001, INFINITY, xi);
+            xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
+            const ClosestHit h = closest_hit(s, nodes, r, 0.001, INFINITY, xi);
             if (h.prim < 0) {
                 key = Q_REGEN;
-                add_radiance(rp, a->pixel, a->thr[0] * float(s.background[0]), a->thr[1] * float(s.background[1]),
-                             a->thr[2] * float(s.background[2]));
+                add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
+                             a.thr[2] * float(s.background[2]));
             } else {
                 PathHit ph; ph.t = h.t; ph.prim = h.prim; ph.pad = 0;
                 *reinterpret_cast<double2*>(w.hits + slot) = *reinterpret_cast<const double2*>(&ph);
                 key = int(s.materials[s.prims[h.prim].material].type);
             }
         }
+        if (next_base + lane < n) {
+            prefetch_l1(w.rays + next_slot);
+            prefetch_l1(w.aux + next_slot);
+        }
         const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
         if (key >= 0) {
             uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
             q[pos] = slot;
         }
+        base = next_base;
+        slot = next_slot;
     }
 }
 
@@ -375,7 +411,7 @@ __global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* 
     MediumXi mx;
     mx.row = xi ? xi + i * s.n_media : nullptr;
     mx.seed = 0; mx.stream = 0; mx.path_lo = uint32_t(i); mx.path_hi = uint32_t(i >> 32); mx.bounce = 0;
-    const ClosestHit h = closest_hit(s, r, t_min, t_max, mx);
+    const ClosestHit h = closest_hit(s, s.nodes, r, t_min, t_max, mx);
     HitRecordOut o;
     if (h.prim < 0) {
         o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
@@ -402,6 +438,8 @@ struct Renderer::Impl {
     std::vector<void*> pool_allocs;
     WaveCounters* counters_host = nullptr;      // pinned
     int sm_count = 148;
+    size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_extend
+    size_t extend_smem_set = 0;
     // adaptive scratch
     uint32_t* list[2] = { nullptr, nullptr };
     uint32_t* tile_list = nullptr;
@@ -441,6 +479,7 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("ARTB_MAX_SHARED_NODES")) impl_->max_shared_nodes = size_t(atoll(e));   // tuning knob (bytes)
     cudaStream_t st;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     stream_ = st;
@@ -484,7 +523,7 @@ void Renderer::upload(const FlatScene& fs)
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (void* p : impl_->scene_allocs) cudaFree(p);
     impl_->scene_allocs.clear();
-    if (fs.bvh_depth >= ARTB_STACK_DEPTH - 1)
+    if (fs.bvh_depth > ARTB_MAX_BVH8_DEPTH)
         throw std::runtime_error("scene BVH is deeper than the device traversal stack");
     uint64_t bytes = 0;
     SceneView v{};
@@ -506,7 +545,6 @@ void Renderer::upload(const FlatScene& fs)
     v.n_textures = uint32_t(fs.textures.size());
     v.n_global_prims = fs.n_global_prims;
     v.n_global_media = fs.n_global_media;
-    v.root = fs.root;
     for (int k = 0; k < 3; ++k) v.background[k] = fs.background[k];
     CUDA_CHECK(cudaStreamSynchronize(st));
     view_ = v;
@@ -625,7 +663,14 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     rp.count = p.adaptive ? count_dev : nullptr;
     rp.lumsq = p.adaptive ? I.lumsq : nullptr;
 
-    const int ext_blocks = I.sm_count * 8, shade_blocks = I.sm_count * 8;
+    const int shade_blocks = I.sm_count * 8;
+    // extend: the node array goes to shared memory when it fits next to a useful amount of L1
+    const size_t node_bytes = size_t(view_.n_nodes) * sizeof(FlatNode8);
+    const bool shared_nodes = node_bytes > 0 && node_bytes <= I.max_shared_nodes;
+    if (shared_nodes && node_bytes > I.extend_smem_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(node_bytes)));
+        I.extend_smem_set = node_bytes;
+    }
     RenderStats S;
     cudaEvent_t ev_begin, ev_end;
     CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
@@ -669,7 +714,8 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     if (pairs_used == kPairs) drain();
                     CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used], st));
                 }
-                k_extend<<<ext_blocks, 128, 0, st>>>(w, view_, rp, cur);
+                if (shared_nodes) k_extend<true><<<I.sm_count, ARTB_EXTEND_THREADS, node_bytes, st>>>(w, view_, rp, cur);
+                else k_extend<false><<<I.sm_count * 8, 128, 0, st>>>(w, view_, rp, cur);
                 if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used + 1], st)); pairs_used++; }
                 S.launches += 2;
                 S.waves++;

@@ -1,6 +1,6 @@
 // rt_intersect.cuh — closest-hit query over the flattened scene (the "extend" stage).
 //
-// Replaces, in one iterative short-stack traversal: hittable_list::hit (hittable_list.cpp:5-19),
+// Replaces, in one iterative traversal of an 8-wide compressed BVH: hittable_list::hit (hittable_list.cpp:5-19),
 // bvh_node::hit + aabb::hit (bvh.cpp:44-52, aabb.h:16-29), box::hit (box.cpp:17-19), translate::hit and
 // rotate_y::hit (hittable.cpp:3-12, 57-85), sphere / moving_sphere / x?_rect / triangle ::hit and
 // constant_medium::hit (constant_medium.h:37-82).
@@ -11,7 +11,8 @@
 // tested last in its depth-first order. Here leaves may be visited in any order: a candidate replaces the
 // current best iff t < best_t or (t == best_t and dfs_id > best_dfs). Primitive formulas are the
 // reference's, evaluated in double in the primitive's object space (transform chains replayed with the
-// reference's arithmetic), so t is the same number up to FMA contraction.
+// reference's arithmetic), so t is the same number up to FMA contraction. Node tests are FP32 and only
+// conservative: they decide how much work is done, never the result.
 #ifndef ARTB_RT_INTERSECT_CUH
 #define ARTB_RT_INTERSECT_CUH
 
@@ -20,10 +21,19 @@
 
 namespace artb {
 
-#define ARTB_STACK_DEPTH 64
+#define ARTB_STACK_DEPTH 32          // uint2 entries; at most 2 per level of 8-wide nodes
+#define ARTB_MAX_BVH8_DEPTH 14
+
+// optional work counters (hostsim / instrumented builds): node visits, primitive tests, medium tests
+struct TraversalStats { unsigned long long nodes, prims, media; };
+#if defined(ARTB_TRAVERSAL_STATS)
+#define ARTB_STAT(s, field) do { if (s) (s)->field++; } while (0)
+#else
+#define ARTB_STAT(s, field) do { } while (0)
+#endif
 
 // ---- transform chains ---------------------------------------------------------------------------
-__device__ __forceinline__ void xform_op_in(const FlatXformOp& op, DRay& r)
+ARTB_HD void xform_op_in(const FlatXformOp& op, DRay& r)
 {
     if (op.type == XFORM_TRANSLATE) {
         // translate::hit — hittable.cpp:4
@@ -38,7 +48,7 @@ __device__ __forceinline__ void xform_op_in(const FlatXformOp& op, DRay& r)
     }
 }
 
-__device__ __forceinline__ DRay to_object_space(const SceneView& s, uint32_t xform, const DRay& world)
+ARTB_HD DRay to_object_space(const SceneView& s, uint32_t xform, const DRay& world)
 {
     DRay r = world;
     if (xform) {
@@ -49,7 +59,7 @@ __device__ __forceinline__ DRay to_object_space(const SceneView& s, uint32_t xfo
 }
 
 // ---- primitive candidates: t only -----------------------------------------------------------------
-__device__ __forceinline__ bool sphere_t(d3 center, double radius, const DRay& r, double t_min, double t_max, double& t)
+ARTB_HD bool sphere_t(d3 center, double radius, const DRay& r, double t_min, double t_max, double& t)
 {
     // sphere.h:40-57
     const d3 oc = r.o - center;
@@ -68,14 +78,14 @@ __device__ __forceinline__ bool sphere_t(d3 center, double radius, const DRay& r
     return true;
 }
 
-__device__ __forceinline__ d3 msphere_center(const FlatPrim& p, double time)
+ARTB_HD d3 msphere_center(const FlatPrim& p, double time)
 {
     // moving_sphere.h:29-31
     const d3 c0 = ld3(p.g), c1 = ld3(p.g + 3);
     return c0 + ((time - p.g[6]) / (p.g[7] - p.g[6])) * (c1 - c0);
 }
 
-__device__ __forceinline__ bool rect_t(uint32_t type, const double* g, const DRay& r, double t_min, double t_max, double& t)
+ARTB_HD bool rect_t(uint32_t type, const double* g, const DRay& r, double t_min, double t_max, double& t)
 {
     // aarect.cpp:3-55; g = a0 a1 b0 b1 k
     double ok, dk, oa, da, ob, db;
@@ -91,7 +101,7 @@ __device__ __forceinline__ bool rect_t(uint32_t type, const double* g, const DRa
     return true;
 }
 
-__device__ __forceinline__ bool triangle_t(const double* g, const DRay& r, double t_min, double t_max, double& t)
+ARTB_HD bool triangle_t(const double* g, const DRay& r, double t_min, double t_max, double& t)
 {
     // triangle.h:28-76
     const d3 pt1 = ld3(g), pt2 = ld3(g + 3), pt3 = ld3(g + 6);
@@ -109,7 +119,7 @@ __device__ __forceinline__ bool triangle_t(const double* g, const DRay& r, doubl
     return true;
 }
 
-__device__ __forceinline__ bool surface_t(const FlatPrim& p, const DRay& r, double t_min, double t_max, double& t)
+ARTB_HD bool surface_t(const FlatPrim& p, const DRay& r, double t_min, double t_max, double& t)
 {
     switch (p.type) {
         case PRIM_SPHERE:   return sphere_t(ld3(p.g), p.g[3], r, t_min, t_max, t);
@@ -120,8 +130,8 @@ __device__ __forceinline__ bool surface_t(const FlatPrim& p, const DRay& r, doub
 }
 
 // closest boundary hit of a medium: hittable::hit of the boundary sub-graph, scanned like a list
-__device__ inline bool boundary_t(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                  double t_min, double t_max, double& t)
+ARTB_HD bool boundary_t(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                        double t_min, double t_max, double& t)
 {
     bool any = false;
     double closest = t_max;
@@ -142,7 +152,7 @@ __device__ inline bool boundary_t(const SceneView& s, uint32_t first, uint32_t c
 struct MediumXi {
     const double* row;       // n_media values for this ray, or nullptr
     uint32_t seed, stream, path_lo, path_hi, bounce;
-    __device__ __forceinline__ double get(uint32_t slot) const
+    ARTB_HD double get(uint32_t slot) const
     {
         if (row) return row[slot];
         Philox g;
@@ -153,15 +163,14 @@ struct MediumXi {
 
 // The two boundary queries of a medium (constant_medium.h:44-47): rec1 = boundary.hit(-inf, inf),
 // rec2 = boundary.hit(rec1.t + 0.0001, inf).
-__device__ __noinline__ bool medium_interval_general(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                                     double& t1, double& t2)
+ARTB_HD_NOINLINE bool medium_interval_general(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
+                                              double& t1, double& t2)
 {
     if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, t1)) return false;
     return boundary_t(s, first, count, world, t1 + 0.0001, INFINITY, t2);
 }
 
-__device__ __forceinline__ bool medium_interval(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                                double& t1, double& t2)
+ARTB_HD bool medium_interval(const SceneView& s, uint32_t first, uint32_t count, const DRay& world, double& t1, double& t2)
 {
     const FlatPrim& b = s.prims[first];
     if (count == 1 && b.type == PRIM_SPHERE) {
@@ -188,8 +197,8 @@ __device__ __forceinline__ bool medium_interval(const SceneView& s, uint32_t fir
     return medium_interval_general(s, first, count, world, t1, t2);
 }
 
-__device__ __forceinline__ bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
-                                         const MediumXi& xi, double& t)
+ARTB_HD bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
+                      const MediumXi& xi, double& t)
 {
     // constant_medium.h:44-69
     const uint32_t first = uint32_t(p.g[1]), count = uint32_t(p.g[2]);
@@ -209,7 +218,7 @@ __device__ __forceinline__ bool medium_t(const SceneView& s, const FlatPrim& p, 
     // |log(u) - __logf(float(u))| <= 1e-6 (1 + |log u|) (2^-21.4 absolute / 3 ulp, plus the rounding of u), so a
     // lower bound of hit_distance that already exceeds the interval is a certain miss; everything else takes the
     // reference's double-precision expression below.
-    const float lf = __logf(float(u));
+    const float lf = fast_logf(float(u));
     const double hit_distance_lo = -p.g[0] * double(-lf - 1e-6f * (1.f - lf));
     if (hit_distance_lo > distance_inside_boundary) return false;
     const double hit_distance = p.g[0] * log(u);
@@ -218,141 +227,258 @@ __device__ __forceinline__ bool medium_t(const SceneView& s, const FlatPrim& p, 
     return true;
 }
 
-// ---- BVH traversal ------------------------------------------------------------------------------
+// ---- closest hit ----------------------------------------------------------------------------------
 struct ClosestHit { double t; int32_t prim; uint32_t dfs; };
 
-// surfaces of one leaf (or of the global list); media never sit in leaves (flatten.cpp: they are all global)
-__device__ __forceinline__ void test_prims(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                           double t_min, ClosestHit& best, uint32_t& cached_xform, DRay& cached_ray)
+ARTB_HD void test_surface(const SceneView& s, uint32_t i, const DRay& world, double t_min, ClosestHit& best)
 {
-    for (uint32_t i = first; i < first + count; ++i) {
-        const FlatPrim& p = s.prims[i];
-        if (p.type == PRIM_MEDIUM) continue;
-        if (p.xform != cached_xform) { cached_ray = to_object_space(s, p.xform, world); cached_xform = p.xform; }
-        double t;
-        if (surface_t(p, cached_ray, t_min, best.t, t) && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
-            best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
-        }
+    const FlatPrim& p = s.prims[i];
+    if (p.type == PRIM_MEDIUM) return;          // media never sit in the tree (flatten.cpp: they are all global)
+    double t;
+    bool ok;
+    if (p.xform) ok = surface_t(p, to_object_space(s, p.xform, world), t_min, best.t, t);
+    else ok = surface_t(p, world, t_min, best.t, t);
+    if (ok && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
+        best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
     }
 }
 
-// Conservative FP32 slab test. The ray is held as inv = fl(1/d) (magnitude clamped to 1e30, so no inf/NaN ever
-// appears) and, per axis, c = fl(o)*inv with an absolute pad |c|*2^-22 that covers the rounding of the origin to
-// float, of c itself and of the fused multiply-add; the near plane subtracts c+pad, the far plane c-pad. A final
-// relative widening by 2^-21 covers the rounding of inv and of the node planes (which the flattener already rounds
-// OUTWARD). The interval can only grow, never shrink: a ray that hits the double-precision box always passes, and
-// since every candidate primitive is then tested in double with the reference's formula, results do not depend on
-// this test at all — only the amount of work does. Inclusive comparison, so equal-t candidates are still visited.
-struct SlabRay {
-    float ix, iy, iz;        // 1/d
-    float nx, ny, nz;        // c + pad  (subtracted on the near plane)
-    float fx, fy, fz;        // c - pad  (subtracted on the far plane)
-    bool px, py, pz;         // direction sign >= 0: near plane is lo
+// Per-ray constants of the FP32 box tests. inv = fl(1/d), magnitude clamped to 1e20 so that no inf/NaN ever appears
+// (a clamped slab interval is the true one scaled towards 0: every box here is at least 2e-9 thick around its
+// primitive, so the clamp cannot cut off a reachable t). c = fl(o) * inv.
+struct BoxRay {
+    float inv[3];
+    float c[3];
+    uint32_t octinv4;        // (7 - octant) in every byte; octant bit 2: dx < 0, bit 1: dy < 0, bit 0: dz < 0
 };
 
-__device__ __forceinline__ void slab_axis(double o, double d, float& inv, float& cn, float& cf, bool& pos)
+ARTB_HD BoxRay make_box_ray(const DRay& r)
 {
-    double id = 1.0 / d;
-    id = fmin(fmax(id, -1e30), 1e30);
-    if (!(id == id)) id = 1e30;
-    inv = float(id);
-    pos = inv >= 0.f;
-    const float c = float(o) * inv;
-    const float pad = fabsf(c) * 2.384185791015625e-07f + 1e-30f;   // 2^-22
-    cn = c + pad;
-    cf = c - pad;
+    BoxRay b;
+    const double o[3] = { r.o.x, r.o.y, r.o.z }, d[3] = { r.d.x, r.d.y, r.d.z };
+    uint32_t oct = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double id = 1.0 / d[a];
+        id = fmin(fmax(id, -1e20), 1e20);
+        if (!(id == id)) id = 1e20;
+        b.inv[a] = float(id);
+        b.c[a] = float(o[a]) * b.inv[a];
+        if (b.inv[a] < 0.f) oct |= 4u >> a;
+    }
+    b.octinv4 = (7u - oct) * 0x01010101u;
+    return b;
 }
 
-__device__ __forceinline__ SlabRay make_slab_ray(const DRay& r)
+// Conservative slab test against an explicit float box (used for the media's world boxes). Error budget as in
+// node8_hits below: planes are exact floats, so the only errors are the roundings of inv, c and the FMA.
+ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best)
 {
-    SlabRay s;
-    slab_axis(r.o.x, r.d.x, s.ix, s.nx, s.fx, s.px);
-    slab_axis(r.o.y, r.d.y, s.iy, s.ny, s.fy, s.py);
-    slab_axis(r.o.z, r.d.z, s.iz, s.nz, s.fz, s.pz);
-    return s;
-}
-
-__device__ __forceinline__ bool slab(const float* lo, const float* hi, const SlabRay& r, float t_min, float t_best, float& enter)
-{
-    const float nx = fmaf(r.px ? lo[0] : hi[0], r.ix, -r.nx), fx = fmaf(r.px ? hi[0] : lo[0], r.ix, -r.fx);
-    const float ny = fmaf(r.py ? lo[1] : hi[1], r.iy, -r.ny), fy = fmaf(r.py ? hi[1] : lo[1], r.iy, -r.fy);
-    const float nz = fmaf(r.pz ? lo[2] : hi[2], r.iz, -r.nz), fz = fmaf(r.pz ? hi[2] : lo[2], r.iz, -r.fz);
-    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_min));
-    float tf = fminf(fminf(fx, fy), fminf(fz, t_best));
-    tn -= fabsf(tn) * 4.76837158203125e-07f;    // 2^-21
-    tf += fabsf(tf) * 4.76837158203125e-07f;
-    enter = tn;
+    float tn = t_min, tf = t_best;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const bool pos = r.inv[a] >= 0.f;
+        const float n = fmaf(pos ? lo[a] : hi[a], r.inv[a], -r.c[a]);
+        const float f = fmaf(pos ? hi[a] : lo[a], r.inv[a], -r.c[a]);
+        const float pad = (fabsf(r.c[a]) + fmaxf(fabsf(n), fabsf(f))) * 4.76837158203125e-07f + 1e-30f;   // 2^-21
+        tn = fmaxf(tn, n - pad);
+        tf = fminf(tf, f + pad);
+    }
     return tn <= tf;
 }
 
-// "while-while" traversal (Aila & Laine 2009): an inner loop that only walks internal nodes until this lane holds
-// a leaf, then an inner loop that only intersects primitives. The lanes of a warp re-converge between the two, so
-// node tests run next to node tests and primitive tests next to primitive tests.
-__device__ __forceinline__ void traverse_bvh(const SceneView& s, const DRay& ray, const SlabRay& sr, double t_min, float t_min_f,
-                                             ClosestHit& best, uint32_t& cached_xform, DRay& cached_ray)
+// One 8-wide node against one ray. Returns the hit mask in the layout the traversal stack uses: bits 24..31 =
+// internal children, placed at 24 + (slot XOR (7-octant)) so that the highest set bit is the child to enter first;
+// bits 0..23 = primitives of the leaf children that were hit, at their offsets from prim_base.
+//
+// Plane parameter on axis a for quantised coordinate q:  t = (p + q*s - o) / d.  Computed as fmaf(v, A, B) with
+//   v = 1 + q*2^-15   (one PRMT drops the byte q into the mantissa of 1.0f — exact, no int->float conversion),
+//   A = 2^15 * s * inv                (exact: powers of two),
+//   B = fmaf(p, inv, -c) - A          (two roundings).
+// Error budget (eps = 2^-24): inv carries (1+eps) twice (1/d in double, then to float), c = fl(fl(o)*inv) carries
+// |c|*2 eps, B carries (|B| + |A|)*eps + |B|*eps, the final FMA |t|*eps, and |t| <= |B| + 2|A| for every plane of the
+// node. All of it is below pad = (|c| + |B| + 2|A|) * 2^-21, which is SUBTRACTED from near planes and ADDED to far
+// planes: the interval only grows. 2|A|*2^-21 is 1/32 of a quantisation cell, so the loosening is invisible next to
+// the quantisation itself.
+ARTB_HD uint32_t node8_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const BoxRay& r,
+                            float t_min, float t_best)
 {
-    float t_best_f = __double2float_ru(best.t);
-    int32_t stack[ARTB_STACK_DEPTH];
-    int sp = 0;
-    int32_t cur = s.root;            // >= 0 internal node, < 0 leaf code
-    const int32_t kDone = 0x7fffffff;
-    while (cur != kDone) {
-        // ---- walk internal nodes until a leaf is in hand
-        while (cur >= 0 && cur != kDone) {
-            const float4* q = reinterpret_cast<const float4*>(s.nodes + cur);
-            const float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-            const float lo0[3] = { a.x, a.y, a.z }, hi0[3] = { a.w, b.x, b.y };
-            const float lo1[3] = { b.z, b.w, c.x }, hi1[3] = { c.y, c.z, c.w };
-            const int32_t c0 = __float_as_int(d.x), c1 = __float_as_int(d.y);
-            float e0, e1;
-            const bool h0 = slab(lo0, hi0, sr, t_min_f, t_best_f, e0);
-            const bool h1 = slab(lo1, hi1, sr, t_min_f, t_best_f, e1);
-            if (h0 && h1) {
-                const bool first0 = e0 <= e1;
-                cur = first0 ? c0 : c1;
-                if (sp < ARTB_STACK_DEPTH) stack[sp++] = first0 ? c1 : c0;
-            } else if (h0) cur = c0;
-            else if (h1) cur = c1;
-            else cur = sp ? stack[--sp] : kDone;
-        }
-        // ---- intersect the leaf
-        if (cur != kDone) {
-            const uint32_t code = uint32_t(~cur);
-            test_prims(s, code >> 3, (code & 7u) + 1u, ray, t_min, best, cached_xform, cached_ray);
-            t_best_f = __double2float_ru(best.t);
-            cur = sp ? stack[--sp] : kDone;
+    float A[3], Bn[3], Bf[3];
+    const float p[3] = { as_float(n0.x), as_float(n0.y), as_float(n0.z) };
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float s15 = as_float((((n0.w >> (8 * a)) & 0xffu) + 15u) << 23);      // 2^15 * cell
+        A[a] = s15 * r.inv[a];
+        const float B = fmaf(p[a], r.inv[a], -r.c[a]) - A[a];
+        const float pad = (fabsf(r.c[a]) + fabsf(B) + 2.f * fabsf(A[a])) * 4.76837158203125e-07f + 1e-30f;
+        Bn[a] = B - pad;
+        Bf[a] = B + pad;
+    }
+    // near planes: lo where the ray travels in +axis, hi otherwise (n2 = qlo.x | qlo.y, n3 = qlo.z | qhi.x, n4 = qhi.y | qhi.z)
+    const bool px = r.inv[0] >= 0.f, py = r.inv[1] >= 0.f, pz = r.inv[2] >= 0.f;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;             // 24..31 have bits 3 and 4 set
+        const uint32_t inner_mask4 = sign_extend_bytes(is_inner4 << 3);
+        const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+        const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+        const uint32_t nx4 = px ? qlox : qhix, fx4 = px ? qhix : qlox;
+        const uint32_t ny4 = py ? qloy : qhiy, fy4 = py ? qhiy : qloy;
+        const uint32_t nz4 = pz ? qloz : qhiz, fz4 = pz ? qhiz : qloz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t sel = 0x7604u | (uint32_t(j) << 4);                       // bytes: 00 | q_j | 80 | 3f
+            const float tnx = fmaf(as_float(byte_perm(nx4, 0x3f800000u, sel)), A[0], Bn[0]);
+            const float tny = fmaf(as_float(byte_perm(ny4, 0x3f800000u, sel)), A[1], Bn[1]);
+            const float tnz = fmaf(as_float(byte_perm(nz4, 0x3f800000u, sel)), A[2], Bn[2]);
+            const float tfx = fmaf(as_float(byte_perm(fx4, 0x3f800000u, sel)), A[0], Bf[0]);
+            const float tfy = fmaf(as_float(byte_perm(fy4, 0x3f800000u, sel)), A[1], Bf[1]);
+            const float tfz = fmaf(as_float(byte_perm(fz4, 0x3f800000u, sel)), A[2], Bf[2]);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_best));
+            if (tn <= tf) {
+                const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+                const uint32_t index = (bit_index4 >> (8 * j)) & 0xffu;
+                hitmask |= bits << index;
+            }
         }
     }
+    return hitmask;
 }
 
-__device__ inline ClosestHit closest_hit(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi)
-{
+// Traversal state of one lane: a node group {x = index of the first internal child, y = pending internal-child bits
+// (24..31) | imask (0..7)} and a primitive group {x = prim_base, y = pending primitive bits (0..23)}; both kinds share
+// the lane's stack. `alive` drops when the stack runs empty.
+struct Traversal {
+    uint2 ng, pg;
+    int sp;
+    float t_best_f;
+    bool alive;
     ClosestHit best;
-    best.t = t_max; best.prim = -1; best.dfs = 0;
-    uint32_t cached_xform = 0;
-    DRay cached_ray = ray;
+};
 
+ARTB_HD void trav_begin(Traversal& tv, double t_max, bool has_tree)
+{
+    tv.ng = make_uint2(0u, has_tree ? 0x80000000u : 0u);      // the root as the only child of a virtual group
+    tv.pg = make_uint2(0u, 0u);
+    tv.sp = 0;
+    tv.best.t = t_max; tv.best.prim = -1; tv.best.dfs = 0;
+    tv.t_best_f = d2f_ru(t_max);
+    tv.alive = true;
+}
+
+// One round of the WARP-SYNCHRONOUS traversal ("while-while" with a vote): the lanes named in `wm` either all take
+// a node step or all take a primitive step, so FP32 box tests run next to box tests and the double-precision
+// primitive tests next to primitive tests. A lane that has found candidate primitives waits (its node work is
+// postponed, which keeps the pruning by best.t sharp); the primitive step is taken as soon as
+// ARTB_PRIM_VOTE_NUM/DEN of the live lanes wait for one, or nobody can take a node step. Returns the ballot of the
+// lanes that still have work. On the host (hostsim) a warp is one lane and the vote is trivially unanimous.
+// NodePtr: const FlatNode8* in global memory, or the copy k_extend staged in shared memory.
+#ifndef ARTB_PRIM_VOTE_NUM
+#define ARTB_PRIM_VOTE_NUM 1
+#define ARTB_PRIM_VOTE_DEN 2
+#endif
+
+template <class NodePtr>
+ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Traversal& tv, uint2* stack, const DRay& ray,
+                            const BoxRay& br, double t_min, float t_min_f, TraversalStats* stats)
+{
+    if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
+        if (tv.sp == 0) tv.alive = false;
+        else {
+            tv.ng = stack[--tv.sp];
+            if (tv.ng.y <= 0x00ffffffu) { tv.pg = tv.ng; tv.ng = make_uint2(0u, 0u); }
+        }
+    }
+    const uint32_t m_alive = warp_ballot(wm, tv.alive);
+    if (m_alive == 0u) return 0u;
+    const bool want_prims = tv.alive && tv.pg.y != 0u;
+    const uint32_t m_prims = warp_ballot(wm, want_prims);
+    if (ARTB_PRIM_VOTE_DEN * pop_count(m_prims) >= ARTB_PRIM_VOTE_NUM * pop_count(m_alive)) {
+        if (want_prims) {
+            do {
+                const int bit = find_msb(tv.pg.y);
+                tv.pg.y &= ~(1u << bit);
+                ARTB_STAT(stats, prims);
+                test_surface(s, tv.pg.x + uint32_t(bit), ray, t_min, tv.best);
+            } while (tv.pg.y);
+            tv.t_best_f = d2f_ru(tv.best.t);
+        }
+    } else if (tv.alive && !want_prims) {
+        // here ng holds at least one internal child: enter the one the ray meets first
+        const uint32_t hits = tv.ng.y;
+        const int bit = find_msb(hits);
+        tv.ng.y &= ~(1u << bit);
+        if (tv.ng.y > 0x00ffffffu && tv.sp < ARTB_STACK_DEPTH) stack[tv.sp++] = tv.ng;
+        const uint32_t slot = uint32_t(bit - 24) ^ (br.octinv4 & 0xffu);
+        const uint32_t rel = uint32_t(pop_count(hits & ~(0xffffffffu << slot) & 0xffu));
+        const uint4* q = reinterpret_cast<const uint4*>(nodes + (tv.ng.x + rel));
+        const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
+        ARTB_STAT(stats, nodes);
+        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f);
+        tv.ng.x = n1.x;
+        tv.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+        tv.pg.x = n1.y;
+        tv.pg.y = hitmask & 0x00ffffffu;
+        if (tv.pg.y) {            // start fetching the first candidate while other lanes keep walking
+            const char* pf = reinterpret_cast<const char*>(s.prims + (tv.pg.x + uint32_t(find_msb(tv.pg.y))));
+            prefetch_l1(pf);
+            prefetch_l1(pf + 64);
+        }
+    }
+    return m_alive;
+}
+
+// global surfaces: tested for every ray before the tree (same work for every lane, and an early t_max)
+ARTB_HD void test_global_surfaces(const SceneView& s, const DRay& ray, double t_min, Traversal& tv, TraversalStats* stats)
+{
     const uint32_t n_surf = s.n_global_prims - s.n_global_media;
-    const SlabRay sr = make_slab_ray(ray);
-    const float t_min_f = __double2float_rd(t_min);
-    // global surfaces first: same work for every lane, and an early t_max for the traversal
-    if (n_surf) test_prims(s, 0, n_surf, ray, t_min, best, cached_xform, cached_ray);
-    if (s.n_world_prims > s.n_global_prims) traverse_bvh(s, ray, sr, t_min, t_min_f, best, cached_xform, cached_ray);
-    // Media last: their candidate t does not depend on the order either, but with the final t_max the
-    // interval is short, a medium whose box starts beyond the closest surface is skipped after six FMAs, and most of
-    // the others leave through the float-logarithm exit of medium_t.
-    for (uint32_t i = n_surf; i < s.n_global_prims; ++i) {
+    for (uint32_t i = 0; i < n_surf; ++i) {
+        ARTB_STAT(stats, prims);
+        test_surface(s, i, ray, t_min, tv.best);
+    }
+    tv.t_best_f = d2f_ru(tv.best.t);
+}
+
+// Media last: their candidate t does not depend on the order either, but with the final t_max the
+// interval is short, a medium whose box starts beyond the closest surface is skipped after six FMAs, and most of
+// the others leave through the float-logarithm exit of medium_t.
+ARTB_HD void test_global_media(const SceneView& s, const DRay& ray, const BoxRay& br, double t_min, float t_min_f,
+                               const MediumXi& xi, ClosestHit& best, TraversalStats* stats)
+{
+    for (uint32_t i = s.n_global_prims - s.n_global_media; i < s.n_global_prims; ++i) {
         const FlatPrim& p = s.prims[i];
-        const float lo[3] = { __double2float_rd(p.g[4]), __double2float_rd(p.g[5]), __double2float_rd(p.g[6]) };
-        const float hi[3] = { __double2float_ru(p.g[7]), __double2float_ru(p.g[8]), __double2float_ru(p.g[9]) };
-        float enter;
-        if (!slab(lo, hi, sr, t_min_f, __double2float_ru(best.t), enter)) continue;
+        const float lo[3] = { d2f_rd(p.g[4]), d2f_rd(p.g[5]), d2f_rd(p.g[6]) };
+        const float hi[3] = { d2f_ru(p.g[7]), d2f_ru(p.g[8]), d2f_ru(p.g[9]) };
+        if (!slab_box(lo, hi, br, t_min_f, d2f_ru(best.t))) continue;
+        ARTB_STAT(stats, media);
         double t;
         if (medium_t(s, p, ray, t_min, best.t, xi, t) && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
             best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
         }
     }
-    return best;
+}
+
+// one ray per lane from start to end (k_trace_batch, hostsim); k_extend drives the same pieces itself so that it
+// can hand a fresh ray to a lane as soon as its old one is finished
+template <class NodePtr>
+ARTB_HD ClosestHit closest_hit(const SceneView& s, NodePtr nodes, const DRay& ray, double t_min, double t_max, const MediumXi& xi,
+                               TraversalStats* stats = nullptr)
+{
+    const uint32_t wm = warp_active_mask();
+    const BoxRay br = make_box_ray(ray);
+    const float t_min_f = d2f_rd(t_min);
+    Traversal tv;
+    trav_begin(tv, t_max, s.n_world_prims > s.n_global_prims);
+    test_global_surfaces(s, ray, t_min, tv, stats);
+    uint2 stack[ARTB_STACK_DEPTH];
+    while (trav_round(s, nodes, wm, tv, stack, ray, br, t_min, t_min_f, stats) != 0u) { }
+    test_global_media(s, ray, br, t_min, t_min_f, xi, tv.best, stats);
+    return tv.best;
 }
 
 } // namespace artb

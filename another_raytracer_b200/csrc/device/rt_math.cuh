@@ -11,7 +11,7 @@
 #ifndef ARTB_RT_MATH_CUH
 #define ARTB_RT_MATH_CUH
 
-#include <cuda_runtime.h>
+#include "rt_portable.cuh"
 #include <stdint.h>
 #include <math.h>
 #include <float.h>
@@ -20,27 +20,27 @@ namespace artb {
 
 struct d3 { double x, y, z; };
 
-__host__ __device__ __forceinline__ d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
-__host__ __device__ __forceinline__ d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__host__ __device__ __forceinline__ d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__host__ __device__ __forceinline__ d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
-__host__ __device__ __forceinline__ d3 operator*(d3 a, d3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
-__host__ __device__ __forceinline__ d3 operator*(double t, d3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
-__host__ __device__ __forceinline__ d3 operator*(d3 a, double t) { return mk3(t * a.x, t * a.y, t * a.z); }
-__host__ __device__ __forceinline__ d3 operator/(d3 a, double t) { const double s = 1 / t; return mk3(s * a.x, s * a.y, s * a.z); }
-__host__ __device__ __forceinline__ double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__host__ __device__ __forceinline__ d3 cross(d3 a, d3 b)
+ARTB_HD d3 mk3(double x, double y, double z) { d3 r; r.x = x; r.y = y; r.z = z; return r; }
+ARTB_HD d3 operator+(d3 a, d3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+ARTB_HD d3 operator-(d3 a, d3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+ARTB_HD d3 operator-(d3 a) { return mk3(-a.x, -a.y, -a.z); }
+ARTB_HD d3 operator*(d3 a, d3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+ARTB_HD d3 operator*(double t, d3 a) { return mk3(t * a.x, t * a.y, t * a.z); }
+ARTB_HD d3 operator*(d3 a, double t) { return mk3(t * a.x, t * a.y, t * a.z); }
+ARTB_HD d3 operator/(d3 a, double t) { const double s = 1 / t; return mk3(s * a.x, s * a.y, s * a.z); }
+ARTB_HD double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+ARTB_HD d3 cross(d3 a, d3 b)
 {
     return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-__host__ __device__ __forceinline__ double length_squared(d3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
-__host__ __device__ __forceinline__ double length(d3 a) { return sqrt(length_squared(a)); }
-__host__ __device__ __forceinline__ d3 unit_vector(d3 a) { return a / length(a); }
-__host__ __device__ __forceinline__ d3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
+ARTB_HD double length_squared(d3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+ARTB_HD double length(d3 a) { return sqrt(length_squared(a)); }
+ARTB_HD d3 unit_vector(d3 a) { return a / length(a); }
+ARTB_HD d3 ld3(const double* p) { return mk3(p[0], p[1], p[2]); }
 
 struct DRay { d3 o, d; double tm; };
 
-__host__ __device__ __forceinline__ d3 ray_at(const DRay& r, double t) { return r.o + t * r.d; }
+ARTB_HD d3 ray_at(const DRay& r, double t) { return r.o + t * r.d; }
 
 // ---- Philox4x32-10 ------------------------------------------------------------------------------
 struct Philox {
@@ -49,13 +49,13 @@ struct Philox {
     double cached;               // second double of the current block
     bool has_cached;
 
-    __host__ __device__ __forceinline__ void init(uint32_t seed, uint32_t stream, uint32_t a, uint32_t b,
+    ARTB_HD void init(uint32_t seed, uint32_t stream, uint32_t a, uint32_t b,
                                                   uint32_t block, uint32_t purpose)
     {
         key0 = seed; key1 = stream; c0 = a; c1 = b; c2 = block; c3 = purpose; has_cached = false; cached = 0.0;
     }
 
-    __host__ __device__ __forceinline__ static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
+    ARTB_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo)
     {
 #if defined(__CUDA_ARCH__)
         hi = __umulhi(a, b); lo = a * b;
@@ -65,7 +65,7 @@ struct Philox {
 #endif
     }
 
-    __host__ __device__ __forceinline__ static double to_unit(uint32_t a, uint32_t b)
+    ARTB_HD static double to_unit(uint32_t a, uint32_t b)
     {
         // 53 random bits -> [0,1)
         const uint64_t bits = ((uint64_t(a) << 32) | uint64_t(b)) >> 11;
@@ -73,7 +73,7 @@ struct Philox {
     }
 
     // one Philox4x32-10 block = two doubles
-    __host__ __device__ __forceinline__ void block(double& u0, double& u1)
+    ARTB_HD void block(double& u0, double& u1)
     {
         uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3, k0 = key0, k1 = key1;
 #pragma unroll
@@ -90,7 +90,7 @@ struct Philox {
         u1 = to_unit(x2, x3);
     }
 
-    __host__ __device__ __forceinline__ double next_double()
+    ARTB_HD double next_double()
     {
         if (has_cached) { has_cached = false; return cached; }
         double u0;

@@ -1,5 +1,6 @@
 #include "flatten.h"
 
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -432,29 +433,155 @@ private:
         return f;
     }
 
-    int32_t child_ref(int t, uint32_t prim_base)   // tnode -> internal node index or leaf code
+    // ---- which binary subtrees become the children of one 8-wide node ---------------------------------------------
+    // Dynamic programme of Ylitie, Karras & Laine (HPG 2017, sec. 4.1) over the binary SAH tree: wide_cost[n][i] is the
+    // least expected number of wide-node visits (sum of half-areas of the wide nodes created) when the subtree of
+    // binary node n is represented by AT MOST i roots, each root being a wide node or a leaf. A wide node at n costs
+    // area(n) plus the best forest of <= 8 roots below it; fewer roots can always stand in for more. Leaves are the
+    // binary tree's leaves (their primitives are not regrouped), so their cost is a constant and left out.
+    std::vector<std::array<double, 9>> wide_cost;
+    std::vector<std::array<int8_t, 9>> wide_split;      // 0: one root here (wide node or leaf), k > 0: k roots from the left child
+
+    void distribute(int n, int roots, double& cost, int& split) const
     {
-        const TNode& k = tnodes[size_t(t)];
-        if (k.left < 0) return ARTB_LEAF_CODE(prim_base + uint32_t(k.first), k.count);
-        return emit_node(t, prim_base);
+        const TNode& t = tnodes[size_t(n)];
+        cost = infinity; split = 1;
+        for (int k = 1; k < roots; ++k) {
+            const double c = wide_cost[size_t(t.left)][size_t(k)] + wide_cost[size_t(t.right)][size_t(roots - k)];
+            if (c < cost) { cost = c; split = k; }
+        }
     }
 
-    int emit_node(int t, uint32_t prim_base)   // internal tnode -> FlatNode index
+    void build_wide_cost()
     {
-        const int me = int(out.nodes.size());
-        out.nodes.emplace_back();
-        std::memset(&out.nodes[size_t(me)], 0, sizeof(FlatNode));
-        const int kids[2] = { tnodes[size_t(t)].left, tnodes[size_t(t)].right };
-        for (int s = 0; s < 2; ++s) {
-            const int32_t ref = child_ref(kids[s], prim_base);
-            const TNode& k = tnodes[size_t(kids[s])];
-            FlatNode& n = out.nodes[size_t(me)];   // re-fetch: the vector may have grown
-            float* lo = s == 0 ? n.lo0 : n.lo1;
-            float* hi = s == 0 ? n.hi0 : n.hi1;
-            for (int a = 0; a < 3; ++a) { lo[a] = round_down(k.box.lo[a]); hi[a] = round_up(k.box.hi[a]); }
-            (s == 0 ? n.child0 : n.child1) = ref;
+        wide_cost.assign(tnodes.size(), {});
+        wide_split.assign(tnodes.size(), {});
+        // children have larger indices than their parents (build_range appends depth first): go backwards
+        for (int n = int(tnodes.size()) - 1; n >= 0; --n) {
+            const TNode& t = tnodes[size_t(n)];
+            auto& c = wide_cost[size_t(n)];
+            auto& sp = wide_split[size_t(n)];
+            if (t.left < 0) {
+                for (int i = 0; i <= 8; ++i) { c[size_t(i)] = 0.0; sp[size_t(i)] = 0; }
+                continue;
+            }
+            double dc; int ds;
+            distribute(n, 8, dc, ds);
+            c[1] = t.box.half_area() + dc;
+            sp[1] = 0;
+            for (int i = 2; i <= 8; ++i) {
+                distribute(n, i, dc, ds);
+                if (dc < c[size_t(i - 1)]) { c[size_t(i)] = dc; sp[size_t(i)] = int8_t(ds); }
+                else { c[size_t(i)] = c[size_t(i - 1)]; sp[size_t(i)] = sp[size_t(i - 1)]; }
+            }
         }
-        return me;
+    }
+
+    // the roots the table chose for subtree n with a budget of `roots`; open_here: n itself is the wide node being
+    // filled, so it must be opened rather than referenced
+    void collect_children(int n, int roots, bool open_here, std::vector<int>& out) const
+    {
+        const TNode& t = tnodes[size_t(n)];
+        if (t.left < 0) { out.push_back(n); return; }
+        int split;
+        if (open_here) { double c; distribute(n, roots, c, split); }
+        else {
+            split = wide_split[size_t(n)][size_t(roots)];
+            if (split == 0) { out.push_back(n); return; }         // a wide node of its own
+            // the entry may have been inherited from a smaller budget: find the budget it was computed for
+            int r = roots;
+            while (r > 2 && wide_cost[size_t(n)][size_t(r)] == wide_cost[size_t(n)][size_t(r - 1)] &&
+                   wide_split[size_t(n)][size_t(r - 1)] == split) --r;
+            roots = r;
+        }
+        collect_children(t.left, split, false, out);
+        collect_children(t.right, roots - split, false, out);
+    }
+
+    // ---- collapse the binary tree into 8-wide compressed nodes (flat_scene.h: FlatNode8) -----------------------
+    void emit_bvh8(int root_t)
+    {
+        struct Job { int tnode; uint32_t node; int depth; };
+        std::vector<Job> queue;
+        out.nodes.emplace_back();
+        queue.push_back({ root_t, 0u, 1 });
+        for (size_t qi = 0; qi < queue.size(); ++qi) {
+            const Job job = queue[qi];
+            out.bvh_depth = std::max(out.bvh_depth, job.depth);
+            // children: the forest of at most eight subtrees the cost table picked for this binary node
+            std::vector<int> kids;
+            const TNode& me = tnodes[size_t(job.tnode)];
+            if (me.left < 0) kids.push_back(job.tnode);
+            else collect_children(job.tnode, 8, true, kids);
+            // slots: a ray of octant o visits slot o first, so slot s wants the child that is nearest along
+            // dir_s = (s&4 ? -1 : +1, s&2 ? -1 : +1, s&1 ? -1 : +1). Greedy assignment on that cost.
+            double centre[3];
+            for (int a = 0; a < 3; ++a) centre[a] = 0.5 * (me.box.lo[a] + me.box.hi[a]);
+            int slot_of[8], kid_in[8];
+            for (int k = 0; k < 8; ++k) { slot_of[k] = -1; kid_in[k] = -1; }
+            for (size_t round = 0; round < kids.size(); ++round) {
+                double best = infinity; int bk = -1, bs = -1;
+                for (size_t k = 0; k < kids.size(); ++k) {
+                    if (slot_of[k] >= 0) continue;
+                    const Box3& cb = tnodes[size_t(kids[k])].box;
+                    for (int sl = 0; sl < 8; ++sl) {
+                        if (kid_in[sl] >= 0) continue;
+                        double cost = 0;
+                        for (int a = 0; a < 3; ++a) {
+                            const double dir = (sl >> (2 - a)) & 1 ? -1.0 : 1.0;
+                            cost += dir * (0.5 * (cb.lo[a] + cb.hi[a]) - centre[a]);
+                        }
+                        if (cost < best) { best = cost; bk = int(k); bs = sl; }
+                    }
+                }
+                slot_of[bk] = bs; kid_in[bs] = bk;
+            }
+            // quantisation grid: origin = box.lo rounded down to float, cell = smallest power of two that keeps
+            // every plane of every child within 255 cells
+            FlatNode8 n;
+            std::memset(&n, 0, sizeof(n));
+            double cell[3];
+            for (int a = 0; a < 3; ++a) {
+                n.p[a] = round_down(me.box.lo[a]);
+                int e = 0;
+                const double extent = me.box.hi[a] - double(n.p[a]);
+                std::frexp(extent / 255.0, &e);                    // extent/255 <= 2^e
+                if (e < -100) e = -100;
+                while (std::ceil(extent / std::ldexp(1.0, e)) > 255.0) ++e;
+                if (e > 100) throw std::logic_error("flatten: scene extent out of range for the quantised BVH");
+                n.e[a] = uint8_t(e + 127);
+                cell[a] = std::ldexp(1.0, e);
+            }
+            n.child_base = uint32_t(out.nodes.size());
+            n.prim_base = uint32_t(out.prims.size());
+            uint32_t prim_offset = 0;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (kid_in[sl] < 0) continue;
+                const int t = kids[size_t(kid_in[sl])];
+                const TNode& c = tnodes[size_t(t)];
+                for (int a = 0; a < 3; ++a) {
+                    double lo = std::floor((c.box.lo[a] - double(n.p[a])) / cell[a]);
+                    double hi = std::ceil((c.box.hi[a] - double(n.p[a])) / cell[a]);
+                    while (double(n.p[a]) + lo * cell[a] > c.box.lo[a]) lo -= 1;     // exact in double: p float, cell 2^e, small integers
+                    while (double(n.p[a]) + hi * cell[a] < c.box.hi[a]) hi += 1;
+                    if (lo < 0 || hi > 255) throw std::logic_error("flatten: quantised BVH box out of range");
+                    n.qlo[a][sl] = uint8_t(lo);
+                    n.qhi[a][sl] = uint8_t(hi);
+                }
+                if (c.left >= 0) {
+                    n.imask = uint8_t(n.imask | (1u << sl));
+                    n.meta[sl] = uint8_t((1u << 5) | (24u + uint32_t(sl)));
+                    queue.push_back({ t, uint32_t(out.nodes.size()), job.depth + 1 });
+                    out.nodes.emplace_back();
+                } else {
+                    if (c.count < 1 || c.count > ARTB_MAX_LEAF_PRIMS) throw std::logic_error("flatten: bad leaf size");
+                    n.meta[sl] = uint8_t((((1u << c.count) - 1u) << 5) | prim_offset);
+                    for (int i = c.first; i < c.first + c.count; ++i) out.prims.push_back(world_items[size_t(order[size_t(i)])].prim);
+                    prim_offset += uint32_t(c.count);
+                }
+            }
+            out.nodes[job.node] = n;
+        }
     }
 
     void build_bvh()
@@ -502,18 +629,18 @@ private:
         out.prims.reserve(world_items.size() + boundary_items.size());
         for (const Item& it : globals) out.prims.push_back(it.prim);
 
-        // 2. binned-SAH tree over the rest
+        // 2. binned-SAH binary tree over the rest, collapsed into 8-wide nodes
         world_items.swap(rest);
         const int n = int(world_items.size());
-        out.root = 0;
         if (n == 0) return;
         if (opt.max_leaf_prims > ARTB_MAX_LEAF_PRIMS) throw std::logic_error("flatten: max_leaf_prims exceeds ARTB_MAX_LEAF_PRIMS");
         order.resize(size_t(n));
         for (int i = 0; i < n; ++i) order[size_t(i)] = i;
         tnodes.reserve(size_t(2 * n));
         const int root = build_range(0, n, 0);
-        for (int i = 0; i < n; ++i) out.prims.push_back(world_items[size_t(order[size_t(i)])].prim);
-        out.root = child_ref(root, out.n_global_prims);
+        out.bvh_depth = 0;
+        build_wide_cost();
+        emit_bvh8(root);
     }
 };
 

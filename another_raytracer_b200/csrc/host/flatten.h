@@ -27,7 +27,7 @@ namespace artb {
 
 struct FlatScene {
     std::vector<FlatPrim> prims;          // [0,n_global) global prims, [n_global,n_world) BVH leaf order, then boundary prims
-    std::vector<FlatNode> nodes;
+    std::vector<FlatNode8> nodes;        // [0] = root (present iff n_world_prims > n_global_prims)
     std::vector<FlatXformOp> xform_ops;
     std::vector<FlatXform> xforms;        // [0] = identity
     std::vector<FlatMaterial> materials;
@@ -41,14 +41,13 @@ struct FlatScene {
     uint32_t n_media = 0;
     uint32_t n_leaves_total = 0;          // dfs ids handed out (reachable or not)
     uint32_t n_culled = 0;
-    int32_t root = 0;                     // internal node index or leaf code (flat_scene.h)
     double background[3] = {0, 0, 0};
     double world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
-    int bvh_depth = 0;
+    int bvh_depth = 0;                    // levels of 8-wide nodes
 };
 
 struct FlattenOptions {
-    int max_leaf_prims = 4;               // <= ARTB_MAX_LEAF_PRIMS
+    int max_leaf_prims = 1;               // <= ARTB_MAX_LEAF_PRIMS; 1: every primitive's own box is tested before its exact test
     double global_area_fraction = 0.25;   // prims whose box half-area exceeds this share of the scene's go to the global list
     int max_global_prims = 8;
     int sah_bins = 16;

@@ -81,7 +81,7 @@ int64_t artb_scene_dump_graph(const artb_scene* s, double* out, int64_t capacity
 /* ---- flattened scene as plain arrays (what a foreign host hands over) ----------------- */
 typedef struct artb_flat_scene {
     const void* prims;      uint32_t n_prims, n_world_prims;   /* FlatPrim[],   96 B each: globals, BVH leaves, boundaries */
-    const void* nodes;      uint32_t n_nodes; int32_t root; uint32_t n_global_prims; int32_t bvh_depth;   /* FlatNode[], 64 B */
+    const void* nodes;      uint32_t n_nodes; int32_t reserved0; uint32_t n_global_prims; int32_t bvh_depth;   /* FlatNode8[], 80 B: 8-wide quantised BVH, [0] = root */
     const void* xform_ops;  uint32_t n_xform_ops;              /* FlatXformOp[], 32 B      */
     const void* xforms;     uint32_t n_xforms;                 /* FlatXform[],    8 B      */
     const void* materials;  uint32_t n_materials;              /* FlatMaterial[], 48 B     */

@@ -472,12 +472,22 @@ ray get_ray(const camera& c, double s, double t)
     return ray(c.origin + offset, c.lower_left_corner + s * c.horizontal + t * c.vertical - c.origin - offset, tm);
 }
 
+// optional log of every closest-hit query of a render (origin, direction, time, remaining depth): lets the tests and
+// tools/ replay realistic ray sets (all bounces of whole paths) through the device traversal
+double* g_ray_log = nullptr;
+std::uint64_t g_ray_log_cap = 0, g_ray_log_n = 0;
+
 // engine::_ray_color: engine.h:447-466
 color ray_color(const ray& r, const color& background, const hittable& world, int depth, query_ctx& q, std::uint64_t* rays)
 {
     hit_record rec;
     if (depth <= 0) return color(0, 0, 0);
     if (rays) ++*rays;
+    if (g_ray_log && g_ray_log_n < g_ray_log_cap) {
+        double* e = g_ray_log + 8 * g_ray_log_n++;
+        for (int k = 0; k < 3; ++k) { e[k] = r.origin()[k]; e[3 + k] = r.direction()[k]; }
+        e[6] = r.time(); e[7] = double(depth);
+    }
     if (!hit_any(world, r, 0.001, infinity, rec, q)) return background;
     ray scattered;
     color attenuation;
@@ -556,6 +566,8 @@ ORACLE_API void* oracle_scene_build(int alias, const char* assets_root)
 ORACLE_API void oracle_scene_free(void* h) { delete static_cast<oracle_scene*>(h); }
 ORACLE_API int oracle_scene_n_media(void* h) { return static_cast<oracle_scene*>(h)->n_media; }
 ORACLE_API int oracle_scene_n_leaves(void* h) { return static_cast<oracle_scene*>(h)->n_leaves; }
+ORACLE_API void oracle_ray_log_begin(double* buf, std::uint64_t capacity) { g_ray_log = buf; g_ray_log_cap = capacity; g_ray_log_n = 0; }
+ORACLE_API std::uint64_t oracle_ray_log_end() { g_ray_log = nullptr; return g_ray_log_n; }
 ORACLE_API double oracle_rng_next() { return random_double(); }
 ORACLE_API void oracle_rng_burn(long n) { for (long i = 0; i < n; ++i) random_double(); }
 // Re-seed the render stream AFTER the scene is built (the scene itself always comes from the default seed, like the

@@ -63,14 +63,33 @@ def test_known_structure_numbers(artb):
 
 
 PRIM = np.dtype([("g", "<f8", 10), ("type", "<u4"), ("material", "<u4"), ("xform", "<u4"), ("dfs_id", "<u4")])
-NODE = np.dtype([("lo0", "<f4", 3), ("hi0", "<f4", 3), ("lo1", "<f4", 3), ("hi1", "<f4", 3),
-                 ("child0", "<i4"), ("child1", "<i4"), ("pad", "<i4", 2)])
+NODE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("prim_base", "<u4"),
+                 ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])       # FlatNode8, csrc/device/flat_scene.h
 
 
-def leaf_range(ref):
-    """child reference < 0 -> (first prim, count); see ARTB_LEAF_CODE in csrc/device/flat_scene.h"""
-    code = (~int(ref)) & 0xFFFFFFFF
-    return code >> 3, (code & 7) + 1
+def node_children(n):
+    """slots of an 8-wide node -> list of (slot, 'node', index) / (slot, 'leaf', first prim, count)"""
+    out, inner = [], 0
+    for sl in range(8):
+        m = int(n["meta"][sl])
+        if m == 0:
+            assert not (int(n["imask"]) >> sl) & 1
+            continue
+        if (m & 0x18) == 0x18:
+            assert m == (1 << 5) | (24 + sl) and (int(n["imask"]) >> sl) & 1
+            out.append((sl, "node", int(n["child_base"]) + inner))
+            inner += 1
+        else:
+            count = {1: 1, 3: 2, 7: 3}[m >> 5]
+            out.append((sl, "leaf", int(n["prim_base"]) + (m & 31), count))
+    return out
+
+
+def child_box(n, sl):
+    cell = np.ldexp(1.0, n["e"].astype(int) - 127)
+    lo = n["p"].astype(np.float64) + n["qlo"][:, sl].astype(np.float64) * cell
+    hi = n["p"].astype(np.float64) + n["qhi"][:, sl].astype(np.float64) * cell
+    return lo, hi
 
 
 def _flat_arrays(scene):
@@ -85,38 +104,44 @@ def _flat_arrays(scene):
 def test_flattened_bvh_invariants(artb, alias):
     s = artb.Scene.build(alias)
     v, prims, nodes = _flat_arrays(s)
-    assert PRIM.itemsize == 96 and NODE.itemsize == 64
+    assert PRIM.itemsize == 96 and NODE.itemsize == 80
     n_world, n_global = v.n_world_prims, v.n_global_prims
-    # every world primitive is either global or referenced by exactly one leaf; dfs ids are unique
+    # every world primitive is either global or referenced by exactly one leaf; every node but the root has one parent
     seen = np.zeros(n_world, dtype=int)
     seen[:n_global] += 1
+    visited = np.zeros(len(nodes), dtype=int)
     depth = 0
     if n_world > n_global:
-        stack = [(v.root, 0)]
+        stack = [(0, 1)]
         while stack:
-            ref, d = stack.pop()
+            idx, d = stack.pop()
+            visited[idx] += 1
             depth = max(depth, d)
-            if ref < 0:
-                first, count = leaf_range(ref)
-                assert first >= n_global and count <= 8
-                seen[first:first + count] += 1
-            else:
-                stack.append((int(nodes[ref]["child0"]), d + 1))
-                stack.append((int(nodes[ref]["child1"]), d + 1))
-    assert np.all(seen == 1)
-    assert depth <= s.info["bvh_depth"] + 1 < 63
+            for ch in node_children(nodes[idx]):
+                if ch[1] == "node":
+                    stack.append((ch[2], d + 1))
+                else:
+                    assert ch[2] >= n_global and ch[3] <= 3
+                    seen[ch[2]:ch[2] + ch[3]] += 1
+    assert np.all(seen == 1) and np.all(visited == 1)
+    assert depth == s.info["bvh_depth"] <= 14
     assert len(np.unique(prims["dfs_id"])) == len(prims)
     assert prims["dfs_id"].max() < s.info["n_leaves_total"]
-    assert np.all(np.diff(prims["dfs_id"][:n_global].astype(np.int64)) > 0)      # globals keep the reference's order
-    # media point at boundary ranges behind the world primitives
-    for p in prims[:n_world][prims["type"][:n_world] == 6]:
+    # globals: surfaces in the reference's order, then every constant_medium of the scene
+    gt = prims["type"][:n_global]
+    n_media = int((gt == 6).sum())
+    assert n_media == s.info["n_media"] and np.all(gt[n_global - n_media:] == 6)
+    assert np.all(np.diff(prims["dfs_id"][:n_global - n_media].astype(np.int64)) > 0)
+    assert np.all(prims["type"][n_global:] != 6)
+    # media point at boundary ranges behind the world primitives and carry their world box in g[4..9]
+    for p in prims[:n_global][gt == 6]:
         first, count = int(p["g"][1]), int(p["g"][2])
         assert n_world <= first and first + count <= len(prims) and count > 0
-    assert np.all(prims["type"][n_world:] != 6)
+        assert np.all(p["g"][4:7] < p["g"][7:10])
 
 
 def test_global_primitive_lists(artb):
-    """scene-spanning primitives are tested up front: the ground sphere of scene 1, the mist of scene 8; tiny scenes
+    """scene-spanning primitives are tested up front: the ground sphere of scene 1, the media of scene 8; tiny scenes
     (Cornell box: 18 rects) have no tree at all above a handful of primitives"""
     s1 = artb.Scene.build(1)
     v, prims, _ = _flat_arrays(s1)
@@ -124,38 +149,57 @@ def test_global_primitive_lists(artb):
     s8 = artb.Scene.build(8)
     v, prims, _ = _flat_arrays(s8)
     g = prims[:v.n_global_prims]
-    assert np.any(g["type"] == 6)
+    assert int((g["type"] == 6).sum()) == 2
     s2 = artb.Scene.build(2)
     v, _, nodes = _flat_arrays(s2)
     assert v.n_global_prims == v.n_world_prims == 2 and len(nodes) == 0
 
 
-def test_child_boxes_bound_their_primitives(artb):
-    """float node boxes (rounded outward) contain the double-precision primitives below them — random scene, identity transforms"""
-    s = artb.Scene.build(1)
+@pytest.mark.parametrize("alias,leaf", [(1, 1), (1, 3), (8, 1), (11, 2)])
+def test_child_boxes_bound_their_primitives(artb, alias, leaf):
+    """quantised child boxes (lo planes rounded down, hi planes up) contain the double-precision boxes of everything
+    below them — checked for untransformed spheres / moving spheres / rects / triangles"""
+    s = artb.Scene.build(alias, max_leaf_prims=leaf)
     v, prims, nodes = _flat_arrays(s)
 
     def prim_box(p):
-        g = p["g"]
-        if p["type"] == 0:
+        g, t = p["g"], int(p["type"])
+        if p["xform"] != 0:
+            return None
+        if t == 0:
             return g[:3] - g[3], g[:3] + g[3]
-        c0, c1, r = g[0:3], g[3:6], g[8]
-        return np.minimum(c0, c1) - r, np.maximum(c0, c1) + r
+        if t == 1:
+            c0, c1, r = g[0:3], g[3:6], g[8]
+            return np.minimum(c0, c1) - r, np.maximum(c0, c1) + r
+        if t == 5:
+            pts = g[:9].reshape(3, 3)
+            return pts.min(axis=0), pts.max(axis=0)
+        a0, a1, b0, b1, k = g[:5]
+        axes = {2: (0, 1, 2), 3: (0, 2, 1), 4: (1, 2, 0)}[t]
+        lo = np.zeros(3); hi = np.zeros(3)
+        lo[axes[0]], hi[axes[0]], lo[axes[1]], hi[axes[1]] = a0, a1, b0, b1
+        lo[axes[2]], hi[axes[2]] = k - 1e-4, k + 1e-4
+        return lo, hi
 
-    def bounds(ref):
-        if ref < 0:
-            first, count = leaf_range(ref)
-            boxes = [prim_box(p) for p in prims[first:first + count]]
-            return np.min([b[0] for b in boxes], axis=0), np.max([b[1] for b in boxes], axis=0)
-        n = nodes[ref]
+    def bounds(idx):
+        n = nodes[idx]
         lo = np.full(3, np.inf); hi = np.full(3, -np.inf)
-        for lo_c, hi_c, c in ((n["lo0"], n["hi0"], n["child0"]), (n["lo1"], n["hi1"], n["child1"])):
-            l, h = bounds(int(c))
-            assert np.all(lo_c.astype(np.float64) <= l) and np.all(hi_c.astype(np.float64) >= h)
+        for ch in node_children(n):
+            blo, bhi = child_box(n, ch[0])
+            assert np.all(blo <= bhi)
+            if ch[1] == "node":
+                l, h = bounds(ch[2])
+            else:
+                boxes = [prim_box(p) for p in prims[ch[2]:ch[2] + ch[3]]]
+                boxes = [b for b in boxes if b is not None]
+                if not boxes:
+                    continue
+                l, h = np.min([b[0] for b in boxes], axis=0), np.max([b[1] for b in boxes], axis=0)
+            assert np.all(blo <= l) and np.all(bhi >= h)
             lo = np.minimum(lo, l); hi = np.maximum(hi, h)
         return lo, hi
 
-    bounds(v.root)
+    bounds(0)
 
 
 def test_zero_thickness_bvh_boxes_are_culled(artb):
@@ -167,7 +211,7 @@ def test_zero_thickness_bvh_boxes_are_culled(artb):
 def test_heightfield_is_one_million_triangles(artb):
     s = artb.Scene.build(12)
     assert s.info["n_world_prims"] == 2 * 707 * 707 + 2
-    assert s.info["bvh_depth"] < 62
+    assert s.info["bvh_depth"] <= 14
 
 
 def test_soup_and_per_triangle_meshes_flatten_to_the_same_geometry(artb):
