@@ -270,6 +270,38 @@ ARTB_HD BoxRay make_box_ray(const DRay& r)
     return b;
 }
 
+// The ray as the FP32 tree walk sees it: origin and direction rounded to float (32 bytes, written next to the
+// double-precision ray by whoever creates it).
+struct ARTB_ALIGN(16) TravRay { float o[3], d[3], tm, pad; };
+
+ARTB_HD TravRay make_trav_ray(const DRay& r)
+{
+    TravRay t;
+    t.o[0] = float(r.o.x); t.o[1] = float(r.o.y); t.o[2] = float(r.o.z);
+    t.d[0] = float(r.d.x); t.d[1] = float(r.d.y); t.d[2] = float(r.d.z);
+    t.tm = float(r.tm); t.pad = 0.f;
+    return t;
+}
+
+// Same constants from the float ray: inv = fl(1/fl(d)) carries the two roundings the error budget of node8_hits
+// allows for, c = fl(o) * inv as above.
+ARTB_HD BoxRay make_box_ray(const TravRay& t)
+{
+    BoxRay b;
+    uint32_t oct = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float id = 1.0f / t.d[a];
+        id = fminf(fmaxf(id, -1e20f), 1e20f);
+        if (!(id == id)) id = 1e20f;
+        b.inv[a] = id;
+        b.c[a] = t.o[a] * id;
+        if (id < 0.f) oct |= 4u >> a;
+    }
+    b.octinv4 = (7u - oct) * 0x01010101u;
+    return b;
+}
+
 // Conservative slab test against an explicit float box (used for the media's world boxes). Error budget as in
 // node8_hits below: planes are exact floats, so the only errors are the roundings of inv, c and the FMA.
 ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best)
@@ -463,6 +495,77 @@ ARTB_HD void test_global_media(const SceneView& s, const DRay& ray, const BoxRay
     }
 }
 
+// ---- two-phase closest hit: FP32 candidate collection, then double-precision confirmation -------------------------
+// Phase 1 (k_traverse) walks the tree with the float ray only and records every primitive whose quantised leaf box
+// the ray enters within [t_min, t_max]: no primitive data, no doubles, no pruning by hits — so the walk is a pure
+// FP32 / shared-memory loop with few registers, and since nothing a lane finds changes what it visits next, lanes can
+// be refilled one by one. (Measured on the reference's scenes: 1.1-1.3x the node visits of the pruned walk.)
+// Phase 2 (k_confirm) runs the reference's double-precision test on exactly those candidates. The box tests are
+// conservative, so every primitive the reference could report is among the candidates, and the closest-hit rule
+// (minimum t, ties to the larger depth-first id) does not depend on the order: the result is the same as the
+// one-phase walk's. A ray with more than ARTB_CAND_CAP candidates is flagged and traced by the one-phase walk.
+#define ARTB_CAND_CAP 15
+#define ARTB_CAND_OVERFLOW 0x80000000u
+struct ARTB_ALIGN(16) CandRec { uint32_t count; uint32_t ids[ARTB_CAND_CAP]; };      // 64 B; count bit 31: overflow
+
+struct Collector { uint2 ng; int sp; uint32_t count; };
+
+ARTB_HD void collect_begin(Collector& c, bool has_tree)
+{
+    c.ng = make_uint2(0u, has_tree ? 0x80000000u : 0u);
+    c.sp = 0;
+    c.count = 0;
+}
+
+// one node visit; false when the walk has ended (tree exhausted, or the candidate list is full: count gets the flag)
+template <class NodePtr>
+ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
+                          uint32_t* ids, TraversalStats* stats)
+{
+    if (c.ng.y <= 0x00ffffffu) {
+        if (c.sp == 0) return false;
+        c.ng = stack[--c.sp];
+    }
+    const uint32_t hits = c.ng.y;
+    const int bit = find_msb(hits);
+    c.ng.y &= ~(1u << bit);
+    if (c.ng.y > 0x00ffffffu && c.sp < ARTB_STACK_DEPTH) stack[c.sp++] = c.ng;
+    const uint32_t slot = uint32_t(bit - 24) ^ (br.octinv4 & 0xffu);
+    const uint32_t rel = uint32_t(pop_count(hits & ~(0xffffffffu << slot) & 0xffu));
+    const uint4* q = reinterpret_cast<const uint4*>(nodes + (c.ng.x + rel));
+    const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
+    ARTB_STAT(stats, nodes);
+    const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f);
+    c.ng.x = n1.x;
+    c.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+    uint32_t m = hitmask & 0x00ffffffu;
+    while (m) {
+        const int b = find_msb(m);
+        m &= ~(1u << b);
+        if (c.count >= ARTB_CAND_CAP) { c.count = ARTB_CAND_CAP | ARTB_CAND_OVERFLOW; return false; }
+        ids[c.count++] = n1.y + uint32_t(b);
+    }
+    return true;
+}
+
+// phase 2 for one ray: global surfaces, the candidates, then the media (order as in closest_hit below)
+ARTB_HD ClosestHit confirm_candidates(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi,
+                                      uint32_t count, const uint32_t* ids, TraversalStats* stats)
+{
+    Traversal tv;
+    trav_begin(tv, t_max, false);
+    test_global_surfaces(s, ray, t_min, tv, stats);
+    for (uint32_t k = 0; k < count; ++k) {
+        ARTB_STAT(stats, prims);
+        test_surface(s, ids[k], ray, t_min, tv.best);
+    }
+    if (s.n_global_media) {
+        const BoxRay br = make_box_ray(ray);
+        test_global_media(s, ray, br, t_min, d2f_rd(t_min), xi, tv.best, stats);
+    }
+    return tv.best;
+}
+
 // one ray per lane from start to end (k_trace_batch, hostsim); k_extend drives the same pieces itself so that it
 // can hand a fresh ray to a lane as soon as its old one is finished
 template <class NodePtr>
@@ -479,6 +582,21 @@ ARTB_HD ClosestHit closest_hit(const SceneView& s, NodePtr nodes, const DRay& ra
     while (trav_round(s, nodes, wm, tv, stack, ray, br, t_min, t_min_f, stats) != 0u) { }
     test_global_media(s, ray, br, t_min, t_min_f, xi, tv.best, stats);
     return tv.best;
+}
+
+// both phases for one ray (hostsim; the kernels run the phases in separate launches)
+template <class NodePtr>
+ARTB_HD ClosestHit closest_hit_two_phase(const SceneView& s, NodePtr nodes, const DRay& ray, double t_min, double t_max,
+                                         const MediumXi& xi, TraversalStats* stats = nullptr)
+{
+    const BoxRay br = make_box_ray(make_trav_ray(ray));
+    Collector c;
+    collect_begin(c, s.n_world_prims > s.n_global_prims);
+    uint2 stack[ARTB_STACK_DEPTH];
+    uint32_t ids[ARTB_CAND_CAP];
+    while (collect_step(nodes, br, d2f_rd(t_min), d2f_ru(t_max), c, stack, ids, stats)) { }
+    if (c.count & ARTB_CAND_OVERFLOW) return closest_hit(s, nodes, ray, t_min, t_max, xi, stats);
+    return confirm_candidates(s, ray, t_min, t_max, xi, c.count, ids, stats);
 }
 
 } // namespace artb

@@ -17,6 +17,9 @@ struct hostsim_hit { double t; int32_t hit; int32_t prim_id; int32_t prim_index;
 // xi: n * n_media explicit medium draws or NULL (Philox keyed by the ray index, as k_trace_batch does).
 // stats_out: 3 counters (node visits, primitive tests, medium tests) summed over the batch, or NULL.
 // per_ray: n * 3 counters (the same three, per ray) or NULL.
+static int g_two_phase = 1;
+void hostsim_set_two_phase(int on) { g_two_phase = on; }
+
 int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, double t_min, double t_max, const double* xi,
                   hostsim_hit* out, unsigned long long* stats_out, uint32_t* per_ray)
 {
@@ -45,7 +48,8 @@ int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, doub
         mx.row = xi ? xi + i * s.n_media : nullptr;
         mx.seed = 0; mx.stream = 0; mx.path_lo = uint32_t(i); mx.path_hi = uint32_t(i >> 32); mx.bounce = 0;
         const TraversalStats before = st;
-        const ClosestHit h = closest_hit(s, s.nodes, r, t_min, t_max, mx, &st);
+        const ClosestHit h = g_two_phase ? closest_hit_two_phase(s, s.nodes, r, t_min, t_max, mx, &st)
+                                         : closest_hit(s, s.nodes, r, t_min, t_max, mx, &st);
         if (per_ray) {
             per_ray[i * 3 + 0] = uint32_t(st.nodes - before.nodes);
             per_ray[i * 3 + 1] = uint32_t(st.prims - before.prims);

@@ -26,14 +26,16 @@ def load():
         lib = C.CDLL(str(LIB))
         lib.hostsim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hostsim_trace.restype = C.c_int
+        lib.hostsim_set_two_phase.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
 
-def trace(scene, rays, t_min=0.001, t_max=float("inf"), xi=None, per_ray=False):
+def trace(scene, rays, t_min=0.001, t_max=float("inf"), xi=None, per_ray=False, two_phase=True):
     """closest hits of `rays` over the flattened `scene` (another_raytracer_b200.Scene); returns (hits, stats);
     per_ray=True adds stats["per_ray"]: (n, 3) node visits / primitive tests / medium tests of every ray"""
     lib = load()
+    lib.hostsim_set_two_phase(int(two_phase))     # True: collect + confirm (what the kernels run); False: the one-phase walk
     view = scene.flat_view()
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
     n = len(rays)

@@ -14,10 +14,11 @@ ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
 
 @pytest.mark.parametrize("alias", ALIASES)
 @pytest.mark.parametrize("leaf", [1, 3])
-def test_hostsim_matches_reference(alias, leaf):
+@pytest.mark.parametrize("two_phase", [True, False])
+def test_hostsim_matches_reference(alias, leaf, two_phase):
     g = np.load(GOLDEN / f"trace_{alias}.npz")
     scene = A.Scene.build(alias, max_leaf_prims=leaf)
-    out, stats = H.trace(scene, g["rays"], 0.001, float("inf"), g["xi"] if int(g["n_media"]) else None)
+    out, stats = H.trace(scene, g["rays"], 0.001, float("inf"), g["xi"] if int(g["n_media"]) else None, two_phase=two_phase)
     h = g["hit"].astype(bool)
     assert np.array_equal(out["hit"].astype(bool), h), "hit / miss decisions differ"
     bad = np.nonzero(out["prim_id"][h] != g["prim"][h])[0]
