@@ -84,7 +84,7 @@ class Stats(C.Structure):
     _fields_ = [("elapsed_ms", C.c_double), ("samples", C.c_uint64), ("rays", C.c_uint64), ("waves", C.c_uint64),
                 ("launches", C.c_uint64), ("extend_ms", C.c_double), ("extend_launches", C.c_uint64),
                 ("pixels_active", C.c_uint64), ("pixels_converged", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64)]
+                ("d2h_bytes", C.c_uint64), ("traverse_ms", C.c_double), ("confirm_ms", C.c_double)]
 
 
 _lib = None

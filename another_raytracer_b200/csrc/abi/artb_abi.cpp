@@ -118,6 +118,7 @@ void to_stats(const RenderStats& s, artb_stats* out)
     out->samples = s.samples; out->rays = s.rays; out->waves = s.waves; out->launches = s.launches;
     out->extend_ms = s.extend_ms; out->extend_launches = s.extend_launches;
     out->pixels_active = s.pixels_active; out->pixels_converged = s.pixels_converged;
+    out->traverse_ms = s.traverse_ms; out->confirm_ms = s.confirm_ms;
 }
 
 } // namespace

@@ -17,6 +17,7 @@
 #include "renderer.h"
 #include "rt_shade.cuh"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -44,7 +45,8 @@ struct __align__(16) PathHit { double t; int32_t prim; int32_t pad; };          
 struct WaveCounters {
     uint32_t n_extend[2];
     uint32_t n_out[2][Q_OUT_COUNT];
-    uint32_t cursor;
+    uint32_t cursor[3];               // chunk cursors of k_traverse, k_confirm and the overflow pass of k_extend
+    uint32_t n_overflow;              // rays whose candidate list overflowed in k_traverse (traced by k_extend)
     uint32_t n_list;                  // pixels in the current round's list
     uint32_t n_next_list;             // adaptive: pixels still unconverged
     unsigned long long issued, total, rays, finished;
@@ -57,6 +59,8 @@ struct WaveBuffers {
     uint32_t* q_extend[2];
     uint32_t* q_regen[2];
     uint32_t* q_shade;                // MAT_COUNT queues of `pool` entries, back to back
+    uint32_t* q_overflow;
+    CandRec* cand;                    // one candidate record per slot (k_traverse -> k_confirm)
     WaveCounters* c;
     uint32_t pool;
 };
@@ -154,7 +158,7 @@ __global__ void k_init_pool(WaveBuffers w)
         for (int k = 0; k < 2; ++k)
             for (int m = 0; m < Q_OUT_COUNT; ++m) c->n_out[k][m] = 0;
         c->n_out[0][Q_REGEN] = w.pool;
-        c->cursor = 0; c->n_list = 0; c->n_next_list = 0;
+        c->cursor[0] = c->cursor[1] = c->cursor[2] = 0; c->n_overflow = 0; c->n_list = 0; c->n_next_list = 0;
         c->issued = c->total = c->rays = c->finished = 0;
     }
 }
@@ -169,25 +173,69 @@ __global__ void k_round_begin(WaveCounters* c, long long n_list_fixed, uint32_t 
     c->total = (unsigned long long)n * batch;
 }
 
-// Closest hit for every ray of q_extend[cur]. Misses add the background and hand their slot to the free list;
-// hits are binned by the material type of the primitive they landed on.
-// kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
-// scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
-// Otherwise (trees beyond the shared-memory budget) nodes are read through L1/L2.
-// (Per-lane refill of finished rays was tried and lost: every stop of the warp to finish / refill a few lanes costs
-// more round trips than the idle lanes it saves; see DESIGN.md.)
-#ifndef ARTB_EXTEND_THREADS
-#define ARTB_EXTEND_THREADS 512
+// =====================================================================================================
+// The closest-hit stage ("extend"), in two kernels + an overflow pass (rt_intersect.cuh "two-phase closest hit"):
+//
+//   k_traverse   FP32 only: walks the 8-wide tree (staged in shared memory when it fits) with the float image of
+//                the ray and writes, per ray, the list of primitives whose leaf box the ray enters. Nothing a lane
+//                finds changes what it visits next, so a finished lane is REFILLED with the next queued ray while
+//                its neighbours keep walking: the warp stays full although per-ray node counts vary 1..40.
+//   k_confirm    the reference's double-precision tests on exactly those candidates. The (ray, candidate) PAIRS of
+//                32 rays are laid out back to back and handed to the lanes 32 at a time, so a ray with 12
+//                candidates and a ray with none keep the same number of lanes busy; every ray's owner lane then
+//                folds the results of its pairs with the reference's rule (smaller t; equal t: later in the
+//                reference's depth-first order). Global surfaces before, media after, as in closest_hit().
+//   k_extend     the one-phase walk (closest_hit) for rays whose candidate list overflowed (none in the
+//                reference's scenes at ARTB_CAND_CAP = 31; grazing rays over huge meshes).
+//
+// The same kernels serve artb_trace_batch (kBatch: explicit rays in, HitRecordOut out), so the parity tests
+// exercise the code the renderer runs.
+// =====================================================================================================
+struct TraceIO {
+    const uint32_t* n_ptr;            // number of rays of this launch (device memory)
+    const uint32_t* list;             // ray ids (path slots); nullptr: 0..n-1
+    CandRec* cand;                    // one record per ray id
+    uint32_t* cursor_traverse;
+    uint32_t* cursor_confirm;
+    uint32_t* q_overflow;
+    uint32_t* n_overflow;
+    double t_min, t_max;
+    const PathRay* rays;              // wave mode: the path pool
+    const PathAux* aux;
+    const double* batch_rays;         // batch mode: n * 7 doubles
+    const double* batch_xi;           // batch mode: n * n_media explicit medium draws, or nullptr
+    HitRecordOut* batch_out;
+};
+
+template <bool kBatch>
+__device__ __forceinline__ DRay trace_io_ray(const TraceIO& io, uint32_t id)
+{
+    if (kBatch) {
+        const double* p = io.batch_rays + size_t(id) * 7;
+        DRay r;
+        r.o = ld3(p); r.d = ld3(p + 3); r.tm = p[6];
+        return r;
+    }
+    return load_ray(io.rays, id);
+}
+
+#ifndef ARTB_TRAVERSE_THREADS
+#define ARTB_TRAVERSE_THREADS 1024
+#endif
+#ifndef ARTB_REFILL_MIN_IDLE
+#define ARTB_REFILL_MIN_IDLE 8        // a warp stops to fetch new rays once this many of its lanes are idle
 #endif
 extern __shared__ uint4 smem_nodes[];
 
-template <bool kShared>
-__global__ void __launch_bounds__(kShared ? ARTB_EXTEND_THREADS : 128, kShared ? 1 : 4)
-k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+// kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
+// scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
+// Otherwise (trees beyond the shared-memory budget) nodes are read through L1/L2.
+template <bool kShared, bool kBatch>
+__global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared ? 1 : 3)
+k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
-    WaveCounters* c = w.c;
-    const uint32_t n = c->n_extend[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t n = *io.n_ptr;
+    if (!kBatch && blockIdx.x == 0 && threadIdx.x == 0) {
         // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
         const unsigned long long left = c->total - c->issued;
         const unsigned long long nr = c->n_out[cur ^ 1][Q_REGEN];
@@ -204,31 +252,228 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
         nodes = reinterpret_cast<const FlatNode8*>(smem_nodes);
     }
     const int lane = threadIdx.x & 31;
-    // Chunks of 32 rays are handed out by an atomic cursor. The grab for the NEXT chunk and the load of its slot ids
-    // are issued before the current chunk is traversed, and its ray records are prefetched before the current
-    // chunk's queue appends, so none of those round trips is waited for.
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&c->cursor, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    uint32_t slot = base + lane < n ? w.q_extend[cur][base + lane] : 0u;
-    while (base < n) {
-        const bool valid = base + lane < n;
-        uint32_t next_base = 0;
-        if (lane == 0) next_base = atomicAdd(&c->cursor, 32u);
-        int key = -1;
-        DRay r;
-        PathAux a;
-        if (valid) {
-            r = load_ray(w.rays, slot);
-            load_aux(w.aux, slot, a);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool has_tree = s.n_world_prims > s.n_global_prims;
+    const float t_min_f = d2f_rd(io.t_min), t_max_f = d2f_ru(io.t_max);
+    uint2 stack[ARTB_STACK_DEPTH];
+    BoxRay br;
+    Collector col;
+    CandRec* rec = nullptr;
+    bool active = false;
+    bool more = true;                 // warp-uniform: the queue may still hold rays
+    collect_begin(col, false);
+    br.inv[0] = br.inv[1] = br.inv[2] = 1.f; br.c[0] = br.c[1] = br.c[2] = 0.f; br.octinv4 = 0u;
+    for (;;) {
+        const uint32_t m_active = __ballot_sync(0xffffffffu, active);
+        const uint32_t idle = ~m_active;
+        if ((more && __popc(idle) >= ARTB_REFILL_MIN_IDLE) || m_active == 0u) {
+            if (!more) break;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(io.cursor_traverse, uint32_t(__popc(idle)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!active) {
+                const uint32_t idx = base + uint32_t(__popc(idle & lt_mask));
+                if (idx < n) {
+                    const uint32_t id = io.list ? io.list[idx] : idx;
+                    const DRay r = trace_io_ray<kBatch>(io, id);
+                    br = make_box_ray(make_trav_ray(r));
+                    collect_begin(col, has_tree);
+                    rec = io.cand + id;
+                    active = true;
+                }
+            }
+            if (base + uint32_t(__popc(idle)) >= n) more = false;
+            continue;
         }
-        next_base = __shfl_sync(0xffffffffu, next_base, 0);
-        const uint32_t next_slot = next_base + lane < n ? w.q_extend[cur][next_base + lane] : 0u;
+        if (active && !collect_step(nodes, br, t_min_f, t_max_f, col, stack, rec->ids, nullptr)) {
+            rec->count = col.count;
+            active = false;
+        }
+    }
+}
+
+#ifndef ARTB_CONFIRM_THREADS
+#define ARTB_CONFIRM_THREADS 256
+#endif
+#ifndef ARTB_CONFIRM_BLOCKS
+#define ARTB_CONFIRM_BLOCKS 2
+#endif
+struct ConfirmWarp {                  // shared-memory scratch of one warp
+    double ray[7][32];                // the 32 rays of the chunk, by lane
+    double res_t[32];                 // results of the current round of pairs (NaN: no hit)
+    uint32_t res_prim[32], res_dfs[32];
+    uint32_t prefix[33];              // exclusive prefix sum of the candidate counts
+    uint32_t id[32];                  // ray ids
+};
+
+template <bool kBatch>
+__global__ void __launch_bounds__(ARTB_CONFIRM_THREADS, ARTB_CONFIRM_BLOCKS)
+k_confirm(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
+{
+    __shared__ ConfirmWarp sh_all[ARTB_CONFIRM_THREADS / 32];
+    const uint32_t n = *io.n_ptr;
+    const int lane = threadIdx.x & 31;
+    ConfirmWarp& sh = sh_all[threadIdx.x >> 5];
+    WaveCounters* c = w.c;
+    const uint32_t n_surf = s.n_global_prims - s.n_global_media;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(io.cursor_confirm, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const uint32_t idx = base + uint32_t(lane);
+        const bool valid = idx < n;
+        uint32_t id = 0, cnt = 0;
+        DRay r;
+        r.o = mk3(0, 0, 0); r.d = mk3(1, 0, 0); r.tm = 0;
         if (valid) {
+            id = io.list ? io.list[idx] : idx;
+            cnt = io.cand[id].count;
+            r = trace_io_ray<kBatch>(io, id);
+        }
+        const bool overflow = (cnt & ARTB_CAND_OVERFLOW) != 0u;
+        if (overflow) cnt = 0;
+        queue_push(io.q_overflow, io.n_overflow, overflow, id, lane);
+        const bool live = valid && !overflow;
+        sh.ray[0][lane] = r.o.x; sh.ray[1][lane] = r.o.y; sh.ray[2][lane] = r.o.z;
+        sh.ray[3][lane] = r.d.x; sh.ray[4][lane] = r.d.y; sh.ray[5][lane] = r.d.z; sh.ray[6][lane] = r.tm;
+        sh.id[lane] = id;
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t excl = incl - cnt;
+        sh.prefix[lane] = excl;
+        if (lane == 31) sh.prefix[32] = incl;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+
+        // this lane's own ray: the global surfaces (same count for every lane)
+        ClosestHit best;
+        best.t = io.t_max; best.prim = -1; best.dfs = 0;
+        if (live)
+            for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
+        __syncwarp();
+
+        // the pairs, 32 at a time
+        for (uint32_t p0 = 0; p0 < total; p0 += 32u) {
+            const uint32_t p = p0 + uint32_t(lane);
+            double t = nan("");
+            uint32_t prim = 0, dfs = 0;
+            if (p < total) {
+                uint32_t o = 0;                       // owner: the last lane whose prefix is <= p
+#pragma unroll
+                for (uint32_t step = 16; step; step >>= 1)
+                    if (sh.prefix[o + step] <= p) o += step;
+                prim = io.cand[sh.id[o]].ids[p - sh.prefix[o]];
+                const FlatPrim& pr = s.prims[prim];
+                dfs = pr.dfs_id;
+                if (pr.type != PRIM_MEDIUM) {         // media never sit in the tree (flatten.cpp: they are all global)
+                    DRay q;
+                    q.o = mk3(sh.ray[0][o], sh.ray[1][o], sh.ray[2][o]);
+                    q.d = mk3(sh.ray[3][o], sh.ray[4][o], sh.ray[5][o]);
+                    q.tm = sh.ray[6][o];
+                    if (pr.xform) q = to_object_space(s, pr.xform, q);
+                    double tt;
+                    if (surface_t(pr, q, io.t_min, io.t_max, tt)) t = tt;
+                }
+            }
+            sh.res_t[lane] = t; sh.res_prim[lane] = prim; sh.res_dfs[lane] = dfs;
+            __syncwarp();
+            const uint32_t lo = excl > p0 ? excl : p0;
+            const uint32_t hi = incl < p0 + 32u ? incl : p0 + 32u;
+            for (uint32_t j = lo; j < hi; ++j) {
+                const double tt = sh.res_t[j - p0];
+                const uint32_t dd = sh.res_dfs[j - p0];
+                if (tt < best.t || (tt == best.t && (best.prim < 0 || dd > best.dfs))) {
+                    best.t = tt; best.prim = int32_t(sh.res_prim[j - p0]); best.dfs = dd;
+                }
+            }
+            __syncwarp();
+        }
+
+        // media last (closest_hit() has the reasons), then the result
+        PathAux a;
+        if (!kBatch && live) load_aux(io.aux, id, a);
+        if (live && s.n_global_media) {
+            MediumXi xi;
+            if (kBatch) {
+                xi.row = io.batch_xi ? io.batch_xi + size_t(id) * s.n_media : nullptr;
+                xi.seed = 0; xi.stream = 0; xi.path_lo = id; xi.path_hi = 0; xi.bounce = 0;
+            } else {
+                xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
+                xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
+            }
+            const BoxRay br = make_box_ray(r);
+            test_global_media(s, r, br, io.t_min, d2f_rd(io.t_min), xi, best, nullptr);
+        }
+        if (kBatch) {
+            if (live) {
+                HitRecordOut o;
+                if (best.prim < 0) {
+                    o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
+                    o.t = o.u = o.v = 0; o.p[0] = o.p[1] = o.p[2] = 0; o.normal[0] = o.normal[1] = o.normal[2] = 0;
+                } else {
+                    const HitInfo hi = make_hit_info(s, best.prim, r, best.t);
+                    o.hit = 1; o.prim_id = int32_t(best.dfs); o.front_face = hi.front_face ? 1 : 0;
+                    o.material_type = int32_t(s.materials[hi.material].type);
+                    o.t = hi.t; o.u = hi.u; o.v = hi.v;
+                    o.p[0] = hi.p.x; o.p[1] = hi.p.y; o.p[2] = hi.p.z;
+                    o.normal[0] = hi.normal.x; o.normal[1] = hi.normal.y; o.normal[2] = hi.normal.z;
+                }
+                io.batch_out[id] = o;
+            }
+        } else {
+            int key = -1;
+            if (live) {
+                if (best.prim < 0) {
+                    key = Q_REGEN;
+                    add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
+                                 a.thr[2] * float(s.background[2]));
+                } else {
+                    PathHit ph; ph.t = best.t; ph.prim = best.prim; ph.pad = 0;
+                    *reinterpret_cast<double2*>(w.hits + id) = *reinterpret_cast<const double2*>(&ph);
+                    key = int(s.materials[s.prims[best.prim].material].type);
+                }
+            }
+            const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
+            if (key >= 0) {
+                uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
+                q[pos] = id;
+            }
+        }
+    }
+}
+
+// The one-phase walk for the rays k_confirm found flagged (candidate list full): closest_hit() per ray, results
+// appended to the same queues. Chunks of 32 rays are handed out by an atomic cursor.
+#ifndef ARTB_EXTEND_THREADS
+#define ARTB_EXTEND_THREADS 128
+#endif
+__global__ void __launch_bounds__(ARTB_EXTEND_THREADS, 4)
+k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+{
+    WaveCounters* c = w.c;
+    const uint32_t n = c->n_overflow;
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&c->cursor[2], 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const bool valid = base + lane < n;
+        const uint32_t slot = valid ? w.q_overflow[base + lane] : 0u;
+        int key = -1;
+        if (valid) {
+            const DRay r = load_ray(w.rays, slot);
+            PathAux a;
+            load_aux(w.aux, slot, a);
             MediumXi xi;
             xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
             xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
-            const ClosestHit h = closest_hit(s, nodes, r, 0.001, INFINITY, xi);
+            const ClosestHit h = closest_hit(s, s.nodes, r, 0.001, INFINITY, xi);
             if (h.prim < 0) {
                 key = Q_REGEN;
                 add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
@@ -239,17 +484,11 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
                 key = int(s.materials[s.prims[h.prim].material].type);
             }
         }
-        if (next_base + lane < n) {
-            prefetch_l1(w.rays + next_slot);
-            prefetch_l1(w.aux + next_slot);
-        }
         const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
         if (key >= 0) {
             uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
             q[pos] = slot;
         }
-        base = next_base;
-        slot = next_slot;
     }
 }
 
@@ -264,7 +503,8 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
         c->n_extend[cur] = 0;
 #pragma unroll
         for (int m = 0; m < MAT_COUNT; ++m) c->n_out[cur ^ 1][m] = 0;
-        c->cursor = 0;
+        c->cursor[0] = c->cursor[1] = c->cursor[2] = 0;
+        c->n_overflow = 0;
     }
     uint32_t start[Q_OUT_COUNT + 1];
     start[0] = 0;
@@ -401,11 +641,13 @@ __global__ void k_resolve(const float* accum, const uint32_t* count, int n_pixel
     }
 }
 
-__global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* rays, uint64_t n, double t_min, double t_max,
-                                                     const double* xi, HitRecordOut* out)
+// one-phase walk over explicit rays: the overflow pass of the batch path (list = the flagged ray indices)
+__global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* rays, const uint32_t* list, uint64_t n,
+                                                     double t_min, double t_max, const double* xi, HitRecordOut* out)
 {
-    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t i = list ? list[j] : j;
     DRay r;
     r.o = ld3(rays + i * 7); r.d = ld3(rays + i * 7 + 3); r.tm = rays[i * 7 + 6];
     MediumXi mx;
@@ -439,7 +681,7 @@ struct Renderer::Impl {
     WaveCounters* counters_host = nullptr;      // pinned
     int sm_count = 148;
     size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_extend
-    size_t extend_smem_set = 0;
+    size_t traverse_smem_set[2] = { 0, 0 };     // [kBatch]
     // adaptive scratch
     uint32_t* list[2] = { nullptr, nullptr };
     uint32_t* tile_list = nullptr;
@@ -447,6 +689,23 @@ struct Renderer::Impl {
     size_t list_capacity = 0;
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> ev;
+
+    // launch helper shared by the renderer and the batch path: the tree walk in shared memory when the node array fits
+    template <bool kBatch>
+    void launch_traverse(const SceneView& view, const TraceIO& io, WaveCounters* c, int cur, cudaStream_t st)
+    {
+        const size_t node_bytes = size_t(view.n_nodes) * sizeof(FlatNode8);
+        if (node_bytes > 0 && node_bytes <= max_shared_nodes) {
+            if (node_bytes > traverse_smem_set[kBatch]) {
+                CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(node_bytes)));
+                traverse_smem_set[kBatch] = node_bytes;
+            }
+            k_traverse<true, kBatch><<<sm_count, ARTB_TRAVERSE_THREADS, node_bytes, st>>>(io, view, c, cur);
+        } else {
+            k_traverse<false, kBatch><<<sm_count * 6, 256, 0, st>>>(io, view, c, cur);
+        }
+        CUDA_CHECK(cudaGetLastError());
+    }
 };
 
 template <class T>
@@ -496,6 +755,8 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
         w.q_regen[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
     }
     w.q_shade = dev_alloc<uint32_t>(impl_->pool_allocs, size_t(pool_paths) * MAT_COUNT);
+    w.q_overflow = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
+    w.cand = dev_alloc<CandRec>(impl_->pool_allocs, pool_paths);
     w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
     CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
 }
@@ -561,14 +822,48 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
     if (n == 0) return 0.f;
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    const unsigned blocks = unsigned((n + 127) / 128);
-    CUDA_CHECK(cudaEventRecord(e0, st));
-    k_trace_batch<<<blocks, 128, 0, st>>>(view_, rays_dev, n, t_min, t_max, xi_dev, out_dev);
-    CUDA_CHECK(cudaEventRecord(e1, st));
-    CUDA_CHECK(cudaGetLastError());
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    std::vector<void*> bag;
     float ms = 0.f;
-    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    try {
+        const uint64_t kChunk = 1u << 22;                         // rays per pass: 512 MB of candidate records
+        const uint64_t cap = std::min<uint64_t>(n, kChunk);
+        CandRec* cand = dev_alloc<CandRec>(bag, cap);
+        uint32_t* overflow = dev_alloc<uint32_t>(bag, cap);
+        uint32_t* ctr = dev_alloc<uint32_t>(bag, 4);              // n, traverse cursor, confirm cursor, overflow count
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        for (uint64_t first = 0; first < n; first += kChunk) {
+            const uint32_t m = uint32_t(std::min<uint64_t>(kChunk, n - first));
+            const uint32_t init[4] = { m, 0u, 0u, 0u };
+            CUDA_CHECK(cudaMemcpyAsync(ctr, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));               // `init` lives on this stack frame
+            TraceIO io{};
+            io.n_ptr = ctr; io.list = nullptr; io.cand = cand;
+            io.cursor_traverse = ctr + 1; io.cursor_confirm = ctr + 2; io.q_overflow = overflow; io.n_overflow = ctr + 3;
+            io.t_min = t_min; io.t_max = t_max;
+            io.batch_rays = rays_dev + first * 7;
+            io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
+            io.batch_out = out_dev + first;
+            impl_->launch_traverse<true>(view_, io, nullptr, 0, st);
+            k_confirm<true><<<impl_->sm_count * 4, ARTB_CONFIRM_THREADS, 0, st>>>(io, view_, impl_->wb, RoundParams{}, 0);
+            CUDA_CHECK(cudaGetLastError());
+            uint32_t n_over = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&n_over, ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (n_over) {
+                k_trace_batch<<<(n_over + 127) / 128, 128, 0, st>>>(view_, io.batch_rays, overflow, n_over, t_min, t_max, io.batch_xi,
+                                                                    io.batch_out);
+                CUDA_CHECK(cudaGetLastError());
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    } catch (...) {
+        for (void* p : bag) cudaFree(p);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        throw;
+    }
+    for (void* p : bag) cudaFree(p);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return ms;
 }
@@ -664,20 +959,14 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     rp.lumsq = p.adaptive ? I.lumsq : nullptr;
 
     const int shade_blocks = I.sm_count * 8;
-    // extend: the node array goes to shared memory when it fits next to a useful amount of L1
-    const size_t node_bytes = size_t(view_.n_nodes) * sizeof(FlatNode8);
-    const bool shared_nodes = node_bytes > 0 && node_bytes <= I.max_shared_nodes;
-    if (shared_nodes && node_bytes > I.extend_smem_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(node_bytes)));
-        I.extend_smem_set = node_bytes;
-    }
     RenderStats S;
     cudaEvent_t ev_begin, ev_end;
     CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
-    // per-launch event pairs for the extend kernel (roofline denominator), drained whenever the pool fills up
-    const size_t kPairs = 2048;
-    if (profile && I.ev.size() < kPairs * 2) {
-        I.ev.resize(kPairs * 2);
+    // per-wave events around the kernels of the closest-hit stage (roofline denominator), drained whenever the pool
+    // fills up: [4k] before k_traverse, [4k+1] after it, [4k+2] after k_confirm, [4k+3] after k_extend
+    const size_t kPairs = 1024;
+    if (profile && I.ev.size() < kPairs * 4) {
+        I.ev.resize(kPairs * 4);
         for (auto& e : I.ev) CUDA_CHECK(cudaEventCreate(&e));
     }
     size_t pairs_used = 0;
@@ -685,8 +974,12 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
         CUDA_CHECK(cudaStreamSynchronize(st));
         for (size_t k = 0; k < pairs_used; ++k) {
             float ms = 0.f;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[2 * k], I.ev[2 * k + 1]));
+            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k], I.ev[4 * k + 3]));
             S.extend_ms += ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k], I.ev[4 * k + 1]));
+            S.traverse_ms += ms;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k + 1], I.ev[4 * k + 2]));
+            S.confirm_ms += ms;
         }
         S.extend_launches += pairs_used;
         pairs_used = 0;
@@ -712,12 +1005,21 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                 cur ^= 1;
                 if (profile) {
                     if (pairs_used == kPairs) drain();
-                    CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used], st));
+                    CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used], st));
                 }
-                if (shared_nodes) k_extend<true><<<I.sm_count, ARTB_EXTEND_THREADS, node_bytes, st>>>(w, view_, rp, cur);
-                else k_extend<false><<<I.sm_count * 8, 128, 0, st>>>(w, view_, rp, cur);
-                if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[2 * pairs_used + 1], st)); pairs_used++; }
-                S.launches += 2;
+                TraceIO io{};
+                io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.cand = w.cand;
+                io.cursor_traverse = &w.c->cursor[0]; io.cursor_confirm = &w.c->cursor[1];
+                io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
+                io.t_min = 0.001; io.t_max = INFINITY;
+                io.rays = w.rays; io.aux = w.aux;
+                I.launch_traverse<false>(view_, io, w.c, cur, st);
+                if (profile) CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 1], st));
+                k_confirm<false><<<I.sm_count * 8, ARTB_CONFIRM_THREADS, 0, st>>>(io, view_, w, rp, cur);
+                if (profile) CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 2], st));
+                k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur);
+                if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 3], st)); pairs_used++; }
+                S.launches += 4;
                 S.waves++;
             }
             CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
@@ -783,17 +1085,26 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
     CUDA_CHECK(cudaSetDevice(device_));
     const size_t n_pixels = size_t(p.width) * size_t(p.height);
     std::vector<void*> bag;
+    const bool dbg = getenv("ARTB_DEBUG_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     try {
         float* d_accum = dev_alloc<float>(bag, n_pixels * 3);
         uint32_t* d_count = dev_alloc<uint32_t>(bag, n_pixels);
         uint8_t* d_rgb = dev_alloc<uint8_t>(bag, n_pixels * 3);
         RenderParams q = p;
         q.accumulate = 0;
+        const double t1 = now();
         render_device(cam, q, d_accum, d_count, stats, false);
+        const double t2 = now();
         resolve_device(d_accum, d_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, d_rgb);
+        const double t3 = now();
         if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, d_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
         if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, d_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
         if (count_out) CUDA_CHECK(cudaMemcpy(count_out, d_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        const double t4 = now();
+        if (dbg) fprintf(stderr, "render_host: alloc %.2f ms, render_device %.2f ms (events %.2f), resolve %.2f ms, d2h %.2f ms\n",
+                         t1 - t0, t2 - t1, stats ? stats->elapsed_ms : 0.0, t3 - t2, t4 - t3);
     } catch (...) {
         for (void* q : bag) cudaFree(q);
         throw;

@@ -36,7 +36,8 @@ struct RenderStats {
     unsigned long long rays = 0;      // closest-hit queries (engine.h:455)
     unsigned long long waves = 0;
     unsigned long long launches = 0;  // kernels launched
-    double extend_ms = 0, shade_ms = 0, generate_ms = 0, other_ms = 0;   // filled when profile=1
+    double extend_ms = 0;             // profile=1: the closest-hit stage (k_traverse + k_confirm + k_extend), per-launch events
+    double traverse_ms = 0, confirm_ms = 0;
     unsigned long long extend_launches = 0;
     unsigned long long pixels_active = 0, pixels_converged = 0;
 };

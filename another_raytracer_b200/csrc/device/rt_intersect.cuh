@@ -504,9 +504,9 @@ ARTB_HD void test_global_media(const SceneView& s, const DRay& ray, const BoxRay
 // conservative, so every primitive the reference could report is among the candidates, and the closest-hit rule
 // (minimum t, ties to the larger depth-first id) does not depend on the order: the result is the same as the
 // one-phase walk's. A ray with more than ARTB_CAND_CAP candidates is flagged and traced by the one-phase walk.
-#define ARTB_CAND_CAP 15
+#define ARTB_CAND_CAP 31
 #define ARTB_CAND_OVERFLOW 0x80000000u
-struct ARTB_ALIGN(16) CandRec { uint32_t count; uint32_t ids[ARTB_CAND_CAP]; };      // 64 B; count bit 31: overflow
+struct ARTB_ALIGN(16) CandRec { uint32_t count; uint32_t ids[ARTB_CAND_CAP]; };      // 128 B; count bit 31: overflow
 
 struct Collector { uint2 ng; int sp; uint32_t count; };
 

@@ -272,6 +272,8 @@ def run_cuda_arm(args, wl):
             opt = A.RenderOptions(W, H, S, seed=args.seed, stream=rank, sample_begin=(1000 + k * world + rank) * S)
             img, st, acc, _ = ctx.render(cam, opt, want_accum=True)    # rgb8 + float sums copied back to the host
             e_samples += st["samples"]
+            if os.environ.get("ARTB_BENCH_DEBUG"):
+                print(f"e2e step {k}: wall so far {time.perf_counter() - te:.3f} s, device {st['elapsed_ms']:.1f} ms", file=sys.stderr)
             h2d += scene.info["flat_bytes"] + st["h2d_bytes"]
             d2h += st["d2h_bytes"]
         barrier()
@@ -298,7 +300,9 @@ def run_cuda_arm(args, wl):
                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rank0_rays / max(ext_launches, 1),
                         "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
-                        "extend_share_of_step": ext_ms / max(sum(s["elapsed_ms"] for s in stats), 1e-9)}
+                        "extend_share_of_step": ext_ms / max(sum(s["elapsed_ms"] for s in stats), 1e-9),
+                        "traverse_ms_per_launch": sum(s["traverse_ms"] for s in stats) / max(ext_launches, 1),
+                        "confirm_ms_per_launch": sum(s["confirm_ms"] for s in stats) / max(ext_launches, 1)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_reference_run(wl, os.cpu_count() or 1)

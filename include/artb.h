@@ -150,6 +150,7 @@ typedef struct artb_stats {
     double extend_ms; uint64_t extend_launches;
     uint64_t pixels_active, pixels_converged;
     uint64_t h2d_bytes, d2h_bytes;
+    double traverse_ms, confirm_ms;     /* profile=1: the two kernels of the closest-hit stage (extend_ms = whole stage) */
 } artb_stats;
 
 /* rgb8_out: W*H*3 bytes, row 0 = top, RGB (the layout engine::run writes). accum_out (optional):

@@ -7,7 +7,7 @@ for lib in another_raytracer_b200/libartb*.so; do
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
-    print(f\"{d['value']:8.1f} Msamples/s  step {d['ms_per_step']:7.2f} ms  extend {r['avg_launch_ms']:.4f} ms/launch  share {r['extend_share_of_step']:.3f}  checksum {d['image_checksum']}\")
+    print(f\"{d['value']:8.1f} Msamples/s  step {d['ms_per_step']:7.2f} ms  extend {r['avg_launch_ms']:.4f} ms/launch  share {r['extend_share_of_step']:.3f}  checksum {d['image_checksum']}  trav {r.get('traverse_ms_per_launch',0):.4f} conf {r.get('confirm_ms_per_launch',0):.4f}\")
 except Exception as e:
     print('FAILED', e)
 "
