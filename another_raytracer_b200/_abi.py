@@ -18,7 +18,7 @@ SYMBOLS = [
     "artb_abi_version", "artb_create", "artb_destroy", "artb_last_error",
     "artb_scene_build", "artb_scene_free", "artb_scene_get_info", "artb_scene_dump_graph", "artb_scene_get_flat",
     "artb_upload_scene", "artb_upload_flat",
-    "artb_trace_batch", "artb_trace_batch_device",
+    "artb_trace_batch", "artb_trace_batch_device", "artb_trace_overflow_rays",
     "artb_render", "artb_render_device", "artb_resolve_device", "artb_stream",
     "artb_save_png", "artb_host_rng_reset", "artb_host_rng_next",
 ]
@@ -84,7 +84,8 @@ class Stats(C.Structure):
     _fields_ = [("elapsed_ms", C.c_double), ("samples", C.c_uint64), ("rays", C.c_uint64), ("waves", C.c_uint64),
                 ("launches", C.c_uint64), ("extend_ms", C.c_double), ("extend_launches", C.c_uint64),
                 ("pixels_active", C.c_uint64), ("pixels_converged", C.c_uint64), ("h2d_bytes", C.c_uint64),
-                ("d2h_bytes", C.c_uint64), ("traverse_ms", C.c_double), ("confirm_ms", C.c_double)]
+                ("d2h_bytes", C.c_uint64), ("traverse_ms", C.c_double), ("pairs_ms", C.c_double), ("finish_ms", C.c_double),
+                ("overflow_rays", C.c_uint64)]
 
 
 _lib = None
@@ -118,6 +119,8 @@ def load() -> C.CDLL:
     lib.artb_upload_flat.argtypes = [vp, C.POINTER(FlatSceneView)]
     lib.artb_trace_batch.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp]
     lib.artb_trace_batch_device.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp, C.POINTER(C.c_float)]
+    lib.artb_trace_overflow_rays.argtypes = [vp]
+    lib.artb_trace_overflow_rays.restype = C.c_uint64
     lib.artb_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, vp, C.POINTER(Stats)]
     lib.artb_render_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, C.POINTER(Stats)]
     lib.artb_resolve_device.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp]

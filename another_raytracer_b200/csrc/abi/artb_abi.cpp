@@ -118,7 +118,7 @@ void to_stats(const RenderStats& s, artb_stats* out)
     out->samples = s.samples; out->rays = s.rays; out->waves = s.waves; out->launches = s.launches;
     out->extend_ms = s.extend_ms; out->extend_launches = s.extend_launches;
     out->pixels_active = s.pixels_active; out->pixels_converged = s.pixels_converged;
-    out->traverse_ms = s.traverse_ms; out->confirm_ms = s.confirm_ms;
+    out->traverse_ms = s.traverse_ms; out->pairs_ms = s.pairs_ms; out->finish_ms = s.finish_ms; out->overflow_rays = s.overflow_rays;
 }
 
 } // namespace
@@ -335,6 +335,11 @@ int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, d
         if (kernel_ms) *kernel_ms = ms;
         return ARTB_OK;
     });
+}
+
+uint64_t artb_trace_overflow_rays(const artb_ctx* ctx)
+{
+    return ctx && ctx->renderer ? ctx->renderer->last_trace_overflow() : 0;
 }
 
 int artb_render(artb_ctx* ctx, const artb_camera* cam, const artb_render_params* p, uint8_t* rgb8_out,

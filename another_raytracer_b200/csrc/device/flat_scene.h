@@ -109,8 +109,19 @@ struct FlatPerlin {       // perlin.h:56-61
 };
 
 // device-side view (all pointers are device pointers)
+// Code path a primitive takes in the double-precision test: k_pairs sorts each tile of pairs by it so that the lanes of
+// a warp run the same test (sphere / moving sphere / rect / triangle, each without or with a transform chain).
+#define ARTB_PRIM_CLASSES 8
+inline uint32_t prim_class_of(uint32_t type, uint32_t xform)
+{
+    const uint32_t path = type == PRIM_SPHERE ? 0u : type == PRIM_MSPHERE ? 1u : type == PRIM_TRIANGLE ? 3u : 2u;
+    return path * 2u + (xform ? 1u : 0u);
+}
+
 struct SceneView {
     const FlatPrim* prims;
+    const uint8_t* prim_class;        // per primitive: prim_class_of(type, xform) (device only; built by Renderer::upload)
+    const uint8_t* prim_mat_type;     // per primitive: type of its material = the shade queue a hit goes to (device only)
     const FlatNode8* nodes;
     const FlatXformOp* xform_ops;
     const FlatXform* xforms;

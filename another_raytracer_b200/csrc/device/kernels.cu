@@ -17,7 +17,6 @@
 #include "renderer.h"
 #include "rt_shade.cuh"
 
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -30,7 +29,7 @@ namespace artb {
 
 struct __align__(16) PathRay { double o[3], d[3], tm, pad; };                       // 64 B
 struct __align__(16) PathAux { float thr[3]; uint32_t pixel, sample, rng_block, depth, pad; };   // 32 B
-struct __align__(16) PathHit { double t; int32_t prim; int32_t pad; };              // 16 B
+struct __align__(16) PathHit { double t; int32_t prim; uint32_t dfs; };             // 16 B: the best hit so far
 
 // Queues written by k_extend (one per material type + the free-slot list) and their counters. Counters are
 // double-buffered by wave parity so that each kernel can reset, from one thread, the counters that NEITHER it nor
@@ -45,13 +44,17 @@ struct __align__(16) PathHit { double t; int32_t prim; int32_t pad; };          
 struct WaveCounters {
     uint32_t n_extend[2];
     uint32_t n_out[2][Q_OUT_COUNT];
-    uint32_t cursor[3];               // chunk cursors of k_traverse, k_confirm and the overflow pass of k_extend
+    uint32_t cursor[3];               // chunk cursors of k_traverse, (unused) and k_extend
     uint32_t n_overflow;              // rays whose candidate list overflowed in k_traverse (traced by k_extend)
     uint32_t n_list;                  // pixels in the current round's list
     uint32_t n_next_list;             // adaptive: pixels still unconverged
-    unsigned long long issued, total, rays, finished;
+    unsigned long long issued, total, rays, finished, overflow_total;
 };
 
+#define ARTB_MAX_REGIONS 1024
+#ifndef ARTB_PAIRS_PER_RAY
+#define ARTB_PAIRS_PER_RAY 8         // capacity of the pair buffer per pool slot (mean over a wave; measured 3-4)
+#endif
 struct WaveBuffers {
     PathRay* rays;
     PathAux* aux;
@@ -60,7 +63,9 @@ struct WaveBuffers {
     uint32_t* q_regen[2];
     uint32_t* q_shade;                // MAT_COUNT queues of `pool` entries, back to back
     uint32_t* q_overflow;
-    CandRec* cand;                    // one candidate record per slot (k_traverse -> k_confirm)
+    uint2* pairs;                     // (ray, primitive) pairs, k_traverse -> k_pairs: pair_capacity entries
+    uint32_t* region_count;           // ARTB_MAX_REGIONS counters
+    size_t pair_capacity;
     WaveCounters* c;
     uint32_t pool;
 };
@@ -159,7 +164,7 @@ __global__ void k_init_pool(WaveBuffers w)
             for (int m = 0; m < Q_OUT_COUNT; ++m) c->n_out[k][m] = 0;
         c->n_out[0][Q_REGEN] = w.pool;
         c->cursor[0] = c->cursor[1] = c->cursor[2] = 0; c->n_overflow = 0; c->n_list = 0; c->n_next_list = 0;
-        c->issued = c->total = c->rays = c->finished = 0;
+        c->issued = c->total = c->rays = c->finished = c->overflow_total = 0;
     }
 }
 
@@ -174,29 +179,40 @@ __global__ void k_round_begin(WaveCounters* c, long long n_list_fixed, uint32_t 
 }
 
 // =====================================================================================================
-// The closest-hit stage ("extend"), in two kernels + an overflow pass (rt_intersect.cuh "two-phase closest hit"):
+// The closest-hit stage ("extend"), as three kernels + an overflow pass (rt_intersect.cuh "two-phase closest hit"):
 //
 //   k_traverse   FP32 only: walks the 8-wide tree (staged in shared memory when it fits) with the float image of
-//                the ray and writes, per ray, the list of primitives whose leaf box the ray enters. Nothing a lane
-//                finds changes what it visits next, so a finished lane is REFILLED with the next queued ray while
-//                its neighbours keep walking: the warp stays full although per-ray node counts vary 1..40.
-//   k_confirm    the reference's double-precision tests on exactly those candidates. The (ray, candidate) PAIRS of
-//                32 rays are laid out back to back and handed to the lanes 32 at a time, so a ray with 12
-//                candidates and a ray with none keep the same number of lanes busy; every ray's owner lane then
-//                folds the results of its pairs with the reference's rule (smaller t; equal t: later in the
-//                reference's depth-first order). Global surfaces before, media after, as in closest_hit().
-//   k_extend     the one-phase walk (closest_hit) for rays whose candidate list overflowed (none in the
-//                reference's scenes at ARTB_CAND_CAP = 31; grazing rays over huge meshes).
+//                the ray and appends a (ray, primitive) PAIR for every primitive whose leaf box the ray enters.
+//                Nothing a lane finds changes what it visits next, so a finished lane is REFILLED with the next
+//                queued ray while its neighbours keep walking: the warp stays full although per-ray node counts
+//                vary 1..40. Pairs go to one region of the pair buffer per block (a shared-memory counter hands out
+//                positions, one atomic per warp and node step), so no global counter is contended.
+//   k_pairs      one thread per PAIR: the reference's double-precision test of that primitive against that ray; a
+//                hit is merged into the ray's 16-byte record {t, prim, dfs} with a 128-bit compare-and-swap under
+//                the reference's rule (smaller t; equal t: later in the reference's depth-first order). A ray with
+//                12 candidates and a ray with one keep the same number of lanes busy.
+//   k_finish     one thread per ray: the global surfaces, then the media (closest_hit() has the reasons for this
+//                order), then misses add the background and free the slot while hits are binned BY MATERIAL TYPE
+//                into the shade queues (warp-aggregated appends).
+//   k_extend     the one-phase walk (closest_hit) for rays whose pairs did not fit their block's region, and for
+//                scenes whose tree is too big for shared memory (there the pruned walk visits far fewer nodes).
 //
 // The same kernels serve artb_trace_batch (kBatch: explicit rays in, HitRecordOut out), so the parity tests
 // exercise the code the renderer runs.
 // =====================================================================================================
+struct PairBuf {
+    uint2* pairs;                     // n_regions * region_cap entries {ray id, primitive index}; ray id ~0: void
+    uint32_t* region_count;           // entries used in every region (written by k_traverse)
+    uint32_t region_cap, n_regions;
+};
+
 struct TraceIO {
     const uint32_t* n_ptr;            // number of rays of this launch (device memory)
     const uint32_t* list;             // ray ids (path slots); nullptr: 0..n-1
-    CandRec* cand;                    // one record per ray id
+    PathHit* hits;                    // one record per ray id: the best hit so far; prim == ARTB_HIT_OVERFLOW: some of the
+                                      // ray's pairs did not fit, the overflow pass traces it
+    PairBuf pb;
     uint32_t* cursor_traverse;
-    uint32_t* cursor_confirm;
     uint32_t* q_overflow;
     uint32_t* n_overflow;
     double t_min, t_max;
@@ -219,6 +235,49 @@ __device__ __forceinline__ DRay trace_io_ray(const TraceIO& io, uint32_t id)
     return load_ray(io.rays, id);
 }
 
+__device__ __forceinline__ PathHit load_hit(const PathHit* h)
+{
+    const double2 v = *reinterpret_cast<const double2*>(h);
+    PathHit r;
+    *reinterpret_cast<double2*>(&r) = v;
+    return r;
+}
+
+#define ARTB_HIT_OVERFLOW (-2)
+__device__ __forceinline__ void mark_overflow(PathHit* h) { h->prim = ARTB_HIT_OVERFLOW; }
+
+__device__ __forceinline__ void store_hit(PathHit* h, double t, int32_t prim, uint32_t dfs)
+{
+    PathHit v; v.t = t; v.prim = prim; v.dfs = dfs;
+    *reinterpret_cast<double2*>(h) = *reinterpret_cast<const double2*>(&v);
+}
+
+// Merge a candidate into a ray's record: 16-byte compare-and-swap loop (ATOMG.CAS.128). Records only ever improve,
+// so a candidate that does not beat a (possibly stale) copy cannot beat the current value either — which is why the
+// caller may read that copy long before the candidate is known (peek_hit next to the primitive and ray loads).
+__device__ __forceinline__ void peek_hit(const PathHit* h, unsigned long long& lo, unsigned long long& hi)
+{
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(h) : "memory");
+}
+
+__device__ __forceinline__ void merge_hit(PathHit* h, unsigned long long cur_lo, unsigned long long cur_hi, double t, uint32_t prim,
+                                          uint32_t dfs)
+{
+    const unsigned long long new_lo = (unsigned long long)__double_as_longlong(t);
+    const unsigned long long new_hi = (unsigned long long)prim | ((unsigned long long)dfs << 32);
+    for (;;) {
+        const double cur_t = __longlong_as_double((long long)cur_lo);
+        if (int32_t(uint32_t(cur_hi)) == ARTB_HIT_OVERFLOW) return;
+        if (!hit_is_better(t, dfs, cur_t, int32_t(uint32_t(cur_hi)), uint32_t(cur_hi >> 32))) return;
+        unsigned long long old_lo, old_hi;
+        asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                     "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                     : "=l"(old_lo), "=l"(old_hi) : "l"(cur_lo), "l"(cur_hi), "l"(new_lo), "l"(new_hi), "l"(h) : "memory");
+        if (old_lo == cur_lo && old_hi == cur_hi) return;
+        cur_lo = old_lo; cur_hi = old_hi;
+    }
+}
+
 #ifndef ARTB_TRAVERSE_THREADS
 #define ARTB_TRAVERSE_THREADS 1024
 #endif
@@ -229,11 +288,12 @@ extern __shared__ uint4 smem_nodes[];
 
 // kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
 // scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
-// Otherwise (trees beyond the shared-memory budget) nodes are read through L1/L2.
+// Otherwise nodes are read through L1/L2.
 template <bool kShared, bool kBatch>
 __global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared ? 1 : 3)
 k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
+    __shared__ uint32_t s_pairs;      // pairs this block has appended to its region
     const uint32_t n = *io.n_ptr;
     if (!kBatch && blockIdx.x == 0 && threadIdx.x == 0) {
         // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
@@ -243,23 +303,29 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
         c->n_out[cur ^ 1][Q_REGEN] = 0;
         c->rays += n;
     }
-    if (n == 0) return;
+    if (n == 0) {
+        if (threadIdx.x == 0) io.pb.region_count[blockIdx.x] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) s_pairs = 0;
     const FlatNode8* nodes = s.nodes;
     if (kShared) {
         const uint4* src = reinterpret_cast<const uint4*>(s.nodes);
         for (uint32_t i = threadIdx.x; i < s.n_nodes * 5u; i += blockDim.x) smem_nodes[i] = __ldg(src + i);
-        __syncthreads();
         nodes = reinterpret_cast<const FlatNode8*>(smem_nodes);
     }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool has_tree = s.n_world_prims > s.n_global_prims;
     const float t_min_f = d2f_rd(io.t_min), t_max_f = d2f_ru(io.t_max);
+    const uint32_t cap = io.pb.region_cap;
+    uint2* region = io.pb.pairs + size_t(blockIdx.x) * cap;
     uint2 stack[ARTB_STACK_DEPTH];
     BoxRay br;
     Collector col;
-    CandRec* rec = nullptr;
-    bool active = false;
+    uint32_t id = 0;
+    bool active = false, spilled = false;
     bool more = true;                 // warp-uniform: the queue may still hold rays
     collect_begin(col, false);
     br.inv[0] = br.inv[1] = br.inv[2] = 1.f; br.c[0] = br.c[1] = br.c[2] = 0.f; br.octinv4 = 0u;
@@ -274,142 +340,194 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
             if (!active) {
                 const uint32_t idx = base + uint32_t(__popc(idle & lt_mask));
                 if (idx < n) {
-                    const uint32_t id = io.list ? io.list[idx] : idx;
+                    id = io.list ? io.list[idx] : idx;
                     const DRay r = trace_io_ray<kBatch>(io, id);
                     br = make_box_ray(make_trav_ray(r));
                     collect_begin(col, has_tree);
-                    rec = io.cand + id;
+                    store_hit(io.hits + id, io.t_max, -1, 0u);
                     active = true;
+                    spilled = false;
                 }
             }
             if (base + uint32_t(__popc(idle)) >= n) more = false;
             continue;
         }
-        if (active && !collect_step(nodes, br, t_min_f, t_max_f, col, stack, rec->ids, nullptr)) {
-            rec->count = col.count;
+        uint32_t prim_base = 0, prim_mask = 0;
+        if (active && !collect_pop(col, stack)) {
+            if (spilled) mark_overflow(io.hits + id);
             active = false;
         }
+        warp_sync();
+        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, nullptr);
+        warp_sync();
+        // append this step's pairs: positions from a warp-wide scan + one shared-memory atomic per warp
+        const uint32_t cnt = uint32_t(__popc(prim_mask));
+        if (__any_sync(0xffffffffu, cnt != 0u)) {
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            uint32_t wbase = 0;
+            if (lane == 31) wbase = atomicAdd(&s_pairs, incl);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            uint32_t pos = wbase + incl - cnt;
+            if (pos + cnt <= cap) {
+                while (prim_mask) {
+                    const int b = find_msb(prim_mask);
+                    prim_mask &= ~(1u << b);
+                    region[pos++] = make_uint2(id, prim_base + uint32_t(b));
+                }
+            } else if (cnt) {
+                spilled = true;                   // region full: void what is left of it, the overflow pass traces the ray
+                for (uint32_t k = 0; k < cnt && pos + k < cap; ++k) region[pos + k] = make_uint2(0xffffffffu, 0u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) io.pb.region_count[blockIdx.x] = s_pairs < cap ? s_pairs : cap;
+}
+
+#ifndef ARTB_PAIRS_THREADS
+#define ARTB_PAIRS_THREADS 256
+#endif
+#ifndef ARTB_PAIRS_BLOCKS
+#define ARTB_PAIRS_BLOCKS 3
+#endif
+#define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory
+template <bool kBatch>
+__global__ void __launch_bounds__(ARTB_PAIRS_THREADS, ARTB_PAIRS_BLOCKS)
+k_pairs(TraceIO io, SceneView s)
+{
+    constexpr uint32_t kTile = ARTB_PAIRS_THREADS * ARTB_PAIRS_PER_THREAD;
+    __shared__ uint2 tile[kTile];
+    __shared__ uint32_t class_count[ARTB_PRIM_CLASSES + 1], class_start[ARTB_PRIM_CLASSES + 1];
+    const uint32_t nr = io.pb.n_regions;
+    const uint32_t r = blockIdx.x % nr, j = blockIdx.x / nr, J = gridDim.x / nr;
+    if (j >= J) return;
+    const uint32_t cnt = io.pb.region_count[r];
+    const uint2* region = io.pb.pairs + size_t(r) * io.pb.region_cap;
+    for (uint32_t t0 = j * kTile; t0 < cnt; t0 += J * kTile) {
+        // 1. load the tile, rank every pair within its class (void pairs and media: class 8, dropped)
+        if (threadIdx.x <= ARTB_PRIM_CLASSES) class_count[threadIdx.x] = 0;
+        __syncthreads();
+        uint2 pr[ARTB_PAIRS_PER_THREAD];
+        uint32_t cls_rank[ARTB_PAIRS_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
+            const uint32_t i = t0 + uint32_t(k) * ARTB_PAIRS_THREADS + threadIdx.x;
+            pr[k] = i < cnt ? region[i] : make_uint2(0xffffffffu, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
+            uint32_t cls = ARTB_PRIM_CLASSES;
+            if (pr[k].x != 0xffffffffu) cls = s.prim_class[pr[k].y];
+            cls_rank[k] = (cls << 24) | atomicAdd(&class_count[cls], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int q = 0; q <= ARTB_PRIM_CLASSES; ++q) { class_start[q] = acc; acc += class_count[q]; }
+        }
+        __syncthreads();
+        // 2. scatter into class order
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
+            const uint32_t cls = cls_rank[k] >> 24;
+            if (cls < ARTB_PRIM_CLASSES) tile[class_start[cls] + (cls_rank[k] & 0xffffffu)] = pr[k];
+        }
+        __syncthreads();
+        const uint32_t n_live = class_start[ARTB_PRIM_CLASSES];
+        // 3. one pair per thread, warps (almost) uniform in class. Warp-uniform trip count and explicit re-convergence
+        // points: the primitive tests have many exits, and without them the compiler clones the merge into every exit.
+        for (uint32_t base = threadIdx.x & ~31u; base < n_live; base += ARTB_PAIRS_THREADS) {
+            const uint32_t i = base + (threadIdx.x & 31u);
+            bool ok = false;
+            double t = 0.0;
+            uint32_t dfs = 0;
+            uint2 pq = make_uint2(0u, 0u);
+            unsigned long long cur_lo = 0, cur_hi = 0;
+            if (i < n_live) {
+                pq = tile[i];
+                peek_hit(io.hits + pq.x, cur_lo, cur_hi);
+                const FlatPrim& p = s.prims[pq.y];
+                dfs = p.dfs_id;
+                DRay q = trace_io_ray<kBatch>(io, pq.x);
+                if (p.xform) q = to_object_space(s, p.xform, q);
+                ok = surface_t(p, q, io.t_min, io.t_max, t);
+            }
+            warp_sync();
+            if (ok && t == t) merge_hit(io.hits + pq.x, cur_lo, cur_hi, t, pq.y, dfs);
+            warp_sync();
+        }
+        __syncthreads();
     }
 }
 
-#ifndef ARTB_CONFIRM_THREADS
-#define ARTB_CONFIRM_THREADS 256
+#ifndef ARTB_FINISH_THREADS
+#define ARTB_FINISH_THREADS 128
 #endif
-#ifndef ARTB_CONFIRM_BLOCKS
-#define ARTB_CONFIRM_BLOCKS 2
+#ifndef ARTB_FINISH_BLOCKS
+#define ARTB_FINISH_BLOCKS 4
 #endif
-struct ConfirmWarp {                  // shared-memory scratch of one warp
-    double ray[7][32];                // the 32 rays of the chunk, by lane
-    double res_t[32];                 // results of the current round of pairs (NaN: no hit)
-    uint32_t res_prim[32], res_dfs[32];
-    uint32_t prefix[33];              // exclusive prefix sum of the candidate counts
-    uint32_t id[32];                  // ray ids
-};
-
 template <bool kBatch>
-__global__ void __launch_bounds__(ARTB_CONFIRM_THREADS, ARTB_CONFIRM_BLOCKS)
-k_confirm(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
+__global__ void __launch_bounds__(ARTB_FINISH_THREADS, ARTB_FINISH_BLOCKS)
+k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 {
-    __shared__ ConfirmWarp sh_all[ARTB_CONFIRM_THREADS / 32];
     const uint32_t n = *io.n_ptr;
     const int lane = threadIdx.x & 31;
-    ConfirmWarp& sh = sh_all[threadIdx.x >> 5];
     WaveCounters* c = w.c;
     const uint32_t n_surf = s.n_global_prims - s.n_global_media;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(io.cursor_confirm, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n) break;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // The ray id of the NEXT iteration is loaded one iteration ahead and its records are prefetched while this
+    // iteration computes; all records of this iteration are requested together, before anything waits on them.
+    uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
+    uint32_t id = 0;
+    if (base + uint32_t(lane) < n) id = io.list ? io.list[base + lane] : base + uint32_t(lane);
+    for (; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
-        uint32_t id = 0, cnt = 0;
+        const uint32_t next_idx = idx + stride;
+        uint32_t next_id = 0;
+        if (next_idx < n) next_id = io.list ? io.list[next_idx] : next_idx;
+        PathHit ph;
+        ph.t = 0; ph.prim = -1; ph.dfs = 0;
         DRay r;
         r.o = mk3(0, 0, 0); r.d = mk3(1, 0, 0); r.tm = 0;
+        PathAux a;
+        a.thr[0] = a.thr[1] = a.thr[2] = 0.f; a.pixel = a.sample = a.rng_block = a.depth = a.pad = 0;
         if (valid) {
-            id = io.list ? io.list[idx] : idx;
-            cnt = io.cand[id].count;
+            ph = load_hit(io.hits + id);
             r = trace_io_ray<kBatch>(io, id);
+            if (!kBatch) load_aux(io.aux, id, a);
         }
-        const bool overflow = (cnt & ARTB_CAND_OVERFLOW) != 0u;
-        if (overflow) cnt = 0;
+        if (next_idx < n) {
+            prefetch_l1(io.hits + next_id);
+            if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
+            else { prefetch_l1(io.rays + next_id); prefetch_l1(io.aux + next_id); }
+        }
+        const bool overflow = ph.prim == ARTB_HIT_OVERFLOW;
         queue_push(io.q_overflow, io.n_overflow, overflow, id, lane);
         const bool live = valid && !overflow;
-        sh.ray[0][lane] = r.o.x; sh.ray[1][lane] = r.o.y; sh.ray[2][lane] = r.o.z;
-        sh.ray[3][lane] = r.d.x; sh.ray[4][lane] = r.d.y; sh.ray[5][lane] = r.d.z; sh.ray[6][lane] = r.tm;
-        sh.id[lane] = id;
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
-        }
-        const uint32_t excl = incl - cnt;
-        sh.prefix[lane] = excl;
-        if (lane == 31) sh.prefix[32] = incl;
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-
-        // this lane's own ray: the global surfaces (same count for every lane)
-        ClosestHit best;
-        best.t = io.t_max; best.prim = -1; best.dfs = 0;
-        if (live)
+        int key = -1;
+        if (live) {
+            ClosestHit best;
+            best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs;
             for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
-        __syncwarp();
-
-        // the pairs, 32 at a time
-        for (uint32_t p0 = 0; p0 < total; p0 += 32u) {
-            const uint32_t p = p0 + uint32_t(lane);
-            double t = nan("");
-            uint32_t prim = 0, dfs = 0;
-            if (p < total) {
-                uint32_t o = 0;                       // owner: the last lane whose prefix is <= p
-#pragma unroll
-                for (uint32_t step = 16; step; step >>= 1)
-                    if (sh.prefix[o + step] <= p) o += step;
-                prim = io.cand[sh.id[o]].ids[p - sh.prefix[o]];
-                const FlatPrim& pr = s.prims[prim];
-                dfs = pr.dfs_id;
-                if (pr.type != PRIM_MEDIUM) {         // media never sit in the tree (flatten.cpp: they are all global)
-                    DRay q;
-                    q.o = mk3(sh.ray[0][o], sh.ray[1][o], sh.ray[2][o]);
-                    q.d = mk3(sh.ray[3][o], sh.ray[4][o], sh.ray[5][o]);
-                    q.tm = sh.ray[6][o];
-                    if (pr.xform) q = to_object_space(s, pr.xform, q);
-                    double tt;
-                    if (surface_t(pr, q, io.t_min, io.t_max, tt)) t = tt;
+            if (s.n_global_media) {
+                MediumXi xi;
+                if (kBatch) {
+                    xi.row = io.batch_xi ? io.batch_xi + size_t(id) * s.n_media : nullptr;
+                    xi.seed = 0; xi.stream = 0; xi.path_lo = id; xi.path_hi = 0; xi.bounce = 0;
+                } else {
+                    xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
+                    xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
                 }
+                const BoxRay br = make_box_ray(make_trav_ray(r));
+                test_global_media(s, r, br, io.t_min, d2f_rd(io.t_min), xi, best, nullptr);
             }
-            sh.res_t[lane] = t; sh.res_prim[lane] = prim; sh.res_dfs[lane] = dfs;
-            __syncwarp();
-            const uint32_t lo = excl > p0 ? excl : p0;
-            const uint32_t hi = incl < p0 + 32u ? incl : p0 + 32u;
-            for (uint32_t j = lo; j < hi; ++j) {
-                const double tt = sh.res_t[j - p0];
-                const uint32_t dd = sh.res_dfs[j - p0];
-                if (tt < best.t || (tt == best.t && (best.prim < 0 || dd > best.dfs))) {
-                    best.t = tt; best.prim = int32_t(sh.res_prim[j - p0]); best.dfs = dd;
-                }
-            }
-            __syncwarp();
-        }
-
-        // media last (closest_hit() has the reasons), then the result
-        PathAux a;
-        if (!kBatch && live) load_aux(io.aux, id, a);
-        if (live && s.n_global_media) {
-            MediumXi xi;
             if (kBatch) {
-                xi.row = io.batch_xi ? io.batch_xi + size_t(id) * s.n_media : nullptr;
-                xi.seed = 0; xi.stream = 0; xi.path_lo = id; xi.path_hi = 0; xi.bounce = 0;
-            } else {
-                xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
-                xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
-            }
-            const BoxRay br = make_box_ray(r);
-            test_global_media(s, r, br, io.t_min, d2f_rd(io.t_min), xi, best, nullptr);
-        }
-        if (kBatch) {
-            if (live) {
                 HitRecordOut o;
                 if (best.prim < 0) {
                     o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
@@ -423,40 +541,51 @@ k_confirm(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
                     o.normal[0] = hi.normal.x; o.normal[1] = hi.normal.y; o.normal[2] = hi.normal.z;
                 }
                 io.batch_out[id] = o;
+            } else if (best.prim < 0) {
+                key = Q_REGEN;
+                add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
+                             a.thr[2] * float(s.background[2]));
+            } else {
+                store_hit(w.hits + id, best.t, best.prim, best.dfs);
+                key = int(s.prim_mat_type[best.prim]);
             }
-        } else {
-            int key = -1;
-            if (live) {
-                if (best.prim < 0) {
-                    key = Q_REGEN;
-                    add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
-                                 a.thr[2] * float(s.background[2]));
-                } else {
-                    PathHit ph; ph.t = best.t; ph.prim = best.prim; ph.pad = 0;
-                    *reinterpret_cast<double2*>(w.hits + id) = *reinterpret_cast<const double2*>(&ph);
-                    key = int(s.materials[s.prims[best.prim].material].type);
-                }
-            }
+        }
+        if (!kBatch) {
             const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
             if (key >= 0) {
                 uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
                 q[pos] = id;
             }
         }
+        id = next_id;
     }
 }
 
-// The one-phase walk for the rays k_confirm found flagged (candidate list full): closest_hit() per ray, results
-// appended to the same queues. Chunks of 32 rays are handed out by an atomic cursor.
+// The one-phase walk: closest_hit() per ray, results appended to the same queues. all = 0: the rays k_finish found
+// flagged (their pairs did not fit); all = 1: every ray of q_extend[cur] (scenes whose tree does not fit in shared
+// memory: there the pruning by the hits found so far saves more than the two-phase split gains). Chunks of 32 rays
+// are handed out by an atomic cursor.
 #ifndef ARTB_EXTEND_THREADS
 #define ARTB_EXTEND_THREADS 128
 #endif
 __global__ void __launch_bounds__(ARTB_EXTEND_THREADS, 4)
-k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
+k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
 {
     WaveCounters* c = w.c;
-    const uint32_t n = c->n_overflow;
+    const uint32_t n = all ? c->n_extend[cur] : c->n_overflow;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (all) {
+            const unsigned long long left = c->total - c->issued;
+            const unsigned long long nr = c->n_out[cur ^ 1][Q_REGEN];
+            c->issued += nr < left ? nr : left;
+            c->n_out[cur ^ 1][Q_REGEN] = 0;
+            c->rays += n;
+        } else {
+            c->overflow_total += n;
+        }
+    }
     if (n == 0) return;
+    const uint32_t* list = all ? w.q_extend[cur] : w.q_overflow;
     const int lane = threadIdx.x & 31;
     for (;;) {
         uint32_t base = 0;
@@ -464,7 +593,7 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n) break;
         const bool valid = base + lane < n;
-        const uint32_t slot = valid ? w.q_overflow[base + lane] : 0u;
+        const uint32_t slot = valid ? list[base + lane] : 0u;
         int key = -1;
         if (valid) {
             const DRay r = load_ray(w.rays, slot);
@@ -479,8 +608,7 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur)
                 add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
                              a.thr[2] * float(s.background[2]));
             } else {
-                PathHit ph; ph.t = h.t; ph.prim = h.prim; ph.pad = 0;
-                *reinterpret_cast<double2*>(w.hits + slot) = *reinterpret_cast<const double2*>(&ph);
+                store_hit(w.hits + slot, h.t, h.prim, h.dfs);
                 key = int(s.materials[s.prims[h.prim].material].type);
             }
         }
@@ -514,17 +642,27 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
     const uint32_t n_list = c->n_list;
     const int lane = threadIdx.x & 31;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < start[Q_OUT_COUNT]; wi += n_warps) {
-        int m = 0;
+    // which queue a warp index belongs to, the lane's entry in it and the slot stored there
+    auto locate = [&](uint32_t wi, int& m, uint32_t& i, bool& valid) -> uint32_t {
+        m = 0;
 #pragma unroll
         for (int k = 1; k < Q_OUT_COUNT; ++k) if (wi >= start[k]) m = k;
-        const uint32_t i = (wi - start[m]) * 32u + uint32_t(lane);
-        const bool valid = i < c->n_out[cur][m];
-        uint32_t slot = 0;
+        i = (wi - start[m]) * 32u + uint32_t(lane);
+        valid = wi < start[Q_OUT_COUNT] && i < c->n_out[cur][m];
+        if (!valid) return 0u;
+        return m == Q_REGEN ? w.q_regen[cur][i] : w.q_shade[size_t(m) * w.pool + i];
+    };
+    // software pipeline: the slot of the NEXT iteration is loaded one iteration ahead and its records are prefetched
+    // while this iteration shades
+    uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int m = 0; uint32_t i = 0; bool valid = false;
+    uint32_t slot = locate(wi, m, i, valid);
+    for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
+        int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
+        const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
         int key = -1;                       // 0: a ray for the next wave, 1: slot is free
         if (m == Q_REGEN) {
             if (valid) {
-                slot = w.q_regen[cur][i];
                 const unsigned long long sidx = issued + i;
                 key = 1;
                 if (sidx < total) {
@@ -548,11 +686,13 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
                 }
             }
         } else if (valid) {
-            slot = w.q_shade[size_t(m) * w.pool + i];
             const DRay r = load_ray(w.rays, slot);
             PathAux a;
             load_aux(w.aux, slot, a);
-            const PathHit ph = w.hits[slot];
+            const PathHit ph = load_hit(w.hits + slot);
+            if (next_valid && next_m != Q_REGEN) {
+                prefetch_l1(w.rays + next_slot); prefetch_l1(w.aux + next_slot); prefetch_l1(w.hits + next_slot);
+            }
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
             key = 1;
@@ -577,6 +717,7 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
         }
         const uint32_t pos = multi_queue_reserve(key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1], lane);
         if (key >= 0) (key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1])[pos] = slot;
+        m = next_m; i = next_i; valid = next_valid; slot = next_slot;
     }
 }
 
@@ -682,6 +823,9 @@ struct Renderer::Impl {
     int sm_count = 148;
     size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_extend
     size_t traverse_smem_set[2] = { 0, 0 };     // [kBatch]
+    // device scratch of render_host (grow-only: cudaMalloc costs tens of milliseconds next to a render)
+    float* host_accum = nullptr; uint32_t* host_count = nullptr; uint8_t* host_rgb = nullptr;
+    size_t host_pixels = 0;
     // adaptive scratch
     uint32_t* list[2] = { nullptr, nullptr };
     uint32_t* tile_list = nullptr;
@@ -690,20 +834,39 @@ struct Renderer::Impl {
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> ev;
 
-    // launch helper shared by the renderer and the batch path: the tree walk in shared memory when the node array fits
-    template <bool kBatch>
-    void launch_traverse(const SceneView& view, const TraceIO& io, WaveCounters* c, int cur, cudaStream_t st)
+    // launch helpers shared by the renderer and the batch path. The tree walk runs in shared memory when the node
+    // array fits; its grid decides how many regions the pair buffer is cut into.
+    bool nodes_fit_shared(const SceneView& view) const
     {
         const size_t node_bytes = size_t(view.n_nodes) * sizeof(FlatNode8);
-        if (node_bytes > 0 && node_bytes <= max_shared_nodes) {
+        return node_bytes <= max_shared_nodes;
+    }
+    void set_pair_buffer(const SceneView& view, TraceIO& io, uint2* pairs, size_t capacity, uint32_t* region_count) const
+    {
+        io.pb.pairs = pairs; io.pb.region_count = region_count;
+        io.pb.n_regions = nodes_fit_shared(view) ? uint32_t(sm_count) : uint32_t(sm_count) * 6u;
+        io.pb.region_cap = uint32_t(std::min<size_t>(capacity / io.pb.n_regions, 0x7fffffffu));
+    }
+    template <bool kBatch>
+    void launch_trace(const SceneView& view, const TraceIO& io, const WaveBuffers& w, const RoundParams& rp, int cur, cudaStream_t st,
+                      cudaEvent_t* ev)
+    {
+        const size_t node_bytes = std::max<size_t>(size_t(view.n_nodes) * sizeof(FlatNode8), 16);
+        if (nodes_fit_shared(view)) {
             if (node_bytes > traverse_smem_set[kBatch]) {
                 CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(node_bytes)));
                 traverse_smem_set[kBatch] = node_bytes;
             }
-            k_traverse<true, kBatch><<<sm_count, ARTB_TRAVERSE_THREADS, node_bytes, st>>>(io, view, c, cur);
+            k_traverse<true, kBatch><<<io.pb.n_regions, ARTB_TRAVERSE_THREADS, node_bytes, st>>>(io, view, w.c, cur);
         } else {
-            k_traverse<false, kBatch><<<sm_count * 6, 256, 0, st>>>(io, view, c, cur);
+            k_traverse<false, kBatch><<<io.pb.n_regions, 256, 0, st>>>(io, view, w.c, cur);
         }
+        if (ev) CUDA_CHECK(cudaEventRecord(ev[0], st));
+        const uint32_t J = std::max(1u, uint32_t(sm_count) * ARTB_PAIRS_BLOCKS / io.pb.n_regions);
+        k_pairs<kBatch><<<io.pb.n_regions * J, ARTB_PAIRS_THREADS, 0, st>>>(io, view);
+        if (ev) CUDA_CHECK(cudaEventRecord(ev[1], st));
+        k_finish<kBatch><<<sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        if (ev) CUDA_CHECK(cudaEventRecord(ev[2], st));
         CUDA_CHECK(cudaGetLastError());
     }
 };
@@ -756,7 +919,9 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     }
     w.q_shade = dev_alloc<uint32_t>(impl_->pool_allocs, size_t(pool_paths) * MAT_COUNT);
     w.q_overflow = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
-    w.cand = dev_alloc<CandRec>(impl_->pool_allocs, pool_paths);
+    w.pair_capacity = size_t(pool_paths) * ARTB_PAIRS_PER_RAY;
+    w.pairs = dev_alloc<uint2>(impl_->pool_allocs, w.pair_capacity);
+    w.region_count = dev_alloc<uint32_t>(impl_->pool_allocs, ARTB_MAX_REGIONS);
     w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
     CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
 }
@@ -771,6 +936,9 @@ Renderer::~Renderer()
     if (impl_->list[1]) cudaFree(impl_->list[1]);
     if (impl_->tile_list) cudaFree(impl_->tile_list);
     if (impl_->lumsq) cudaFree(impl_->lumsq);
+    if (impl_->host_accum) cudaFree(impl_->host_accum);
+    if (impl_->host_count) cudaFree(impl_->host_count);
+    if (impl_->host_rgb) cudaFree(impl_->host_rgb);
     if (impl_->counters_host) cudaFreeHost(impl_->counters_host);
     for (cudaEvent_t e : impl_->ev) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
@@ -789,6 +957,13 @@ void Renderer::upload(const FlatScene& fs)
     uint64_t bytes = 0;
     SceneView v{};
     v.prims = dev_upload(impl_->scene_allocs, fs.prims, st, bytes);
+    std::vector<uint8_t> prim_class(fs.prims.size());
+    for (size_t i = 0; i < fs.prims.size(); ++i) prim_class[i] = uint8_t(prim_class_of(fs.prims[i].type, fs.prims[i].xform));
+    v.prim_class = dev_upload(impl_->scene_allocs, prim_class, st, bytes);
+    std::vector<uint8_t> prim_mat_type(fs.prims.size());
+    for (size_t i = 0; i < fs.prims.size(); ++i)
+        prim_mat_type[i] = fs.prims[i].material < fs.materials.size() ? uint8_t(fs.materials[fs.prims[i].material].type) : uint8_t(0);
+    v.prim_mat_type = dev_upload(impl_->scene_allocs, prim_mat_type, st, bytes);
     v.nodes = dev_upload(impl_->scene_allocs, fs.nodes, st, bytes);
     v.xform_ops = dev_upload(impl_->scene_allocs, fs.xform_ops, st, bytes);
     v.xforms = dev_upload(impl_->scene_allocs, fs.xforms, st, bytes);
@@ -825,11 +1000,15 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
     std::vector<void*> bag;
     float ms = 0.f;
     try {
-        const uint64_t kChunk = 1u << 22;                         // rays per pass: 512 MB of candidate records
+        const uint64_t kChunk = 1u << 22;                         // rays per pass
         const uint64_t cap = std::min<uint64_t>(n, kChunk);
-        CandRec* cand = dev_alloc<CandRec>(bag, cap);
+        const size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
+        PathHit* hits = dev_alloc<PathHit>(bag, cap);
+        uint2* pairs = dev_alloc<uint2>(bag, pair_capacity);
+        uint32_t* region_count = dev_alloc<uint32_t>(bag, ARTB_MAX_REGIONS);
         uint32_t* overflow = dev_alloc<uint32_t>(bag, cap);
-        uint32_t* ctr = dev_alloc<uint32_t>(bag, 4);              // n, traverse cursor, confirm cursor, overflow count
+        uint32_t* ctr = dev_alloc<uint32_t>(bag, 4);              // n, traverse cursor, -, overflow count
+        last_trace_overflow_ = 0;
         CUDA_CHECK(cudaEventRecord(e0, st));
         for (uint64_t first = 0; first < n; first += kChunk) {
             const uint32_t m = uint32_t(std::min<uint64_t>(kChunk, n - first));
@@ -837,18 +1016,18 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
             CUDA_CHECK(cudaMemcpyAsync(ctr, init, sizeof(init), cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaStreamSynchronize(st));               // `init` lives on this stack frame
             TraceIO io{};
-            io.n_ptr = ctr; io.list = nullptr; io.cand = cand;
-            io.cursor_traverse = ctr + 1; io.cursor_confirm = ctr + 2; io.q_overflow = overflow; io.n_overflow = ctr + 3;
+            io.n_ptr = ctr; io.list = nullptr; io.hits = hits;
+            impl_->set_pair_buffer(view_, io, pairs, pair_capacity, region_count);
+            io.cursor_traverse = ctr + 1; io.q_overflow = overflow; io.n_overflow = ctr + 3;
             io.t_min = t_min; io.t_max = t_max;
             io.batch_rays = rays_dev + first * 7;
             io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
             io.batch_out = out_dev + first;
-            impl_->launch_traverse<true>(view_, io, nullptr, 0, st);
-            k_confirm<true><<<impl_->sm_count * 4, ARTB_CONFIRM_THREADS, 0, st>>>(io, view_, impl_->wb, RoundParams{}, 0);
-            CUDA_CHECK(cudaGetLastError());
+            impl_->launch_trace<true>(view_, io, impl_->wb, RoundParams{}, 0, st, nullptr);
             uint32_t n_over = 0;
             CUDA_CHECK(cudaMemcpyAsync(&n_over, ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
+            last_trace_overflow_ += n_over;
             if (n_over) {
                 k_trace_batch<<<(n_over + 127) / 128, 128, 0, st>>>(view_, io.batch_rays, overflow, n_over, t_min, t_max, io.batch_xi,
                                                                     io.batch_out);
@@ -959,14 +1138,17 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     rp.lumsq = p.adaptive ? I.lumsq : nullptr;
 
     const int shade_blocks = I.sm_count * 8;
+    // two kernels per phase when the tree fits in shared memory, else the pruned one-phase walk (see k_extend)
+    bool two_phase = I.nodes_fit_shared(view_);
+    if (const char* e = getenv("ARTB_TWO_PHASE")) two_phase = atoi(e) != 0;
     RenderStats S;
     cudaEvent_t ev_begin, ev_end;
     CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
     // per-wave events around the kernels of the closest-hit stage (roofline denominator), drained whenever the pool
-    // fills up: [4k] before k_traverse, [4k+1] after it, [4k+2] after k_confirm, [4k+3] after k_extend
+    // fills up: [5k] before k_traverse, [5k+1] after it, [5k+2] after k_pairs, [5k+3] after k_finish, [5k+4] after k_extend
     const size_t kPairs = 1024;
-    if (profile && I.ev.size() < kPairs * 4) {
-        I.ev.resize(kPairs * 4);
+    if (profile && I.ev.size() < kPairs * 5) {
+        I.ev.resize(kPairs * 5);
         for (auto& e : I.ev) CUDA_CHECK(cudaEventCreate(&e));
     }
     size_t pairs_used = 0;
@@ -974,12 +1156,16 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
         CUDA_CHECK(cudaStreamSynchronize(st));
         for (size_t k = 0; k < pairs_used; ++k) {
             float ms = 0.f;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k], I.ev[4 * k + 3]));
+            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k], I.ev[5 * k + 4]));
             S.extend_ms += ms;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k], I.ev[4 * k + 1]));
-            S.traverse_ms += ms;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[4 * k + 1], I.ev[4 * k + 2]));
-            S.confirm_ms += ms;
+            if (two_phase) {
+                CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k], I.ev[5 * k + 1]));
+                S.traverse_ms += ms;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k + 1], I.ev[5 * k + 2]));
+                S.pairs_ms += ms;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k + 2], I.ev[5 * k + 3]));
+                S.finish_ms += ms;
+            }
         }
         S.extend_launches += pairs_used;
         pairs_used = 0;
@@ -1005,21 +1191,24 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                 cur ^= 1;
                 if (profile) {
                     if (pairs_used == kPairs) drain();
-                    CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used], st));
+                    CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used], st));
                 }
-                TraceIO io{};
-                io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.cand = w.cand;
-                io.cursor_traverse = &w.c->cursor[0]; io.cursor_confirm = &w.c->cursor[1];
-                io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
-                io.t_min = 0.001; io.t_max = INFINITY;
-                io.rays = w.rays; io.aux = w.aux;
-                I.launch_traverse<false>(view_, io, w.c, cur, st);
-                if (profile) CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 1], st));
-                k_confirm<false><<<I.sm_count * 8, ARTB_CONFIRM_THREADS, 0, st>>>(io, view_, w, rp, cur);
-                if (profile) CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 2], st));
-                k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur);
-                if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[4 * pairs_used + 3], st)); pairs_used++; }
-                S.launches += 4;
+                if (two_phase) {
+                    TraceIO io{};
+                    io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits;
+                    I.set_pair_buffer(view_, io, w.pairs, w.pair_capacity, w.region_count);
+                    io.cursor_traverse = &w.c->cursor[0];
+                    io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
+                    io.t_min = 0.001; io.t_max = INFINITY;
+                    io.rays = w.rays; io.aux = w.aux;
+                    I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr);
+                    k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);
+                    S.launches += 5;
+                } else {
+                    k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 1);
+                    S.launches += 2;
+                }
+                if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 4], st)); pairs_used++; }
                 S.waves++;
             }
             CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
@@ -1075,6 +1264,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     S.elapsed_ms = ms;
     CUDA_CHECK(cudaMemcpy(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost));
     S.rays = I.counters_host->rays;
+    S.overflow_rays = I.counters_host->overflow_total;
     cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
     if (stats) *stats = S;
 }
@@ -1084,32 +1274,24 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
 {
     CUDA_CHECK(cudaSetDevice(device_));
     const size_t n_pixels = size_t(p.width) * size_t(p.height);
-    std::vector<void*> bag;
-    const bool dbg = getenv("ARTB_DEBUG_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t0 = now();
-    try {
-        float* d_accum = dev_alloc<float>(bag, n_pixels * 3);
-        uint32_t* d_count = dev_alloc<uint32_t>(bag, n_pixels);
-        uint8_t* d_rgb = dev_alloc<uint8_t>(bag, n_pixels * 3);
-        RenderParams q = p;
-        q.accumulate = 0;
-        const double t1 = now();
-        render_device(cam, q, d_accum, d_count, stats, false);
-        const double t2 = now();
-        resolve_device(d_accum, d_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, d_rgb);
-        const double t3 = now();
-        if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, d_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
-        if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, d_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-        if (count_out) CUDA_CHECK(cudaMemcpy(count_out, d_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        const double t4 = now();
-        if (dbg) fprintf(stderr, "render_host: alloc %.2f ms, render_device %.2f ms (events %.2f), resolve %.2f ms, d2h %.2f ms\n",
-                         t1 - t0, t2 - t1, stats ? stats->elapsed_ms : 0.0, t3 - t2, t4 - t3);
-    } catch (...) {
-        for (void* q : bag) cudaFree(q);
-        throw;
+    Impl& I = *impl_;
+    if (I.host_pixels < n_pixels) {
+        if (I.host_accum) cudaFree(I.host_accum);
+        if (I.host_count) cudaFree(I.host_count);
+        if (I.host_rgb) cudaFree(I.host_rgb);
+        I.host_accum = nullptr; I.host_count = nullptr; I.host_rgb = nullptr; I.host_pixels = 0;
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.host_accum), n_pixels * 3 * sizeof(float)));
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.host_count), n_pixels * sizeof(uint32_t)));
+        CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.host_rgb), n_pixels * 3));
+        I.host_pixels = n_pixels;
     }
-    for (void* q : bag) cudaFree(q);
+    RenderParams q = p;
+    q.accumulate = 0;
+    render_device(cam, q, I.host_accum, I.host_count, stats, false);
+    resolve_device(I.host_accum, I.host_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, I.host_rgb);
+    if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, I.host_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
+    if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, I.host_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (count_out) CUDA_CHECK(cudaMemcpy(count_out, I.host_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 }
 
 } // namespace artb

@@ -37,7 +37,8 @@ struct RenderStats {
     unsigned long long waves = 0;
     unsigned long long launches = 0;  // kernels launched
     double extend_ms = 0;             // profile=1: the closest-hit stage (k_traverse + k_confirm + k_extend), per-launch events
-    double traverse_ms = 0, confirm_ms = 0;
+    double traverse_ms = 0, pairs_ms = 0, finish_ms = 0;
+    unsigned long long overflow_rays = 0;   // rays whose candidate list overflowed (traced by the one-phase pass)
     unsigned long long extend_launches = 0;
     unsigned long long pixels_active = 0, pixels_converged = 0;
 };
@@ -53,6 +54,7 @@ public:
     bool has_scene() const { return has_scene_; }
     uint32_t n_media() const { return view_.n_media; }
     uint64_t scene_bytes() const { return scene_bytes_; }
+    uint64_t last_trace_overflow() const { return last_trace_overflow_; }   // rays of the last trace_batch that took the one-phase pass
 
     // parity hook: closest hit for explicit rays. rays = n*7 doubles (o, d, time), xi = n*n_media or null.
     void trace_batch(const double* rays_host, uint64_t n, double t_min, double t_max, const double* xi_host,
@@ -82,6 +84,7 @@ private:
     bool has_scene_ = false;
     SceneView view_{};
     uint64_t scene_bytes_ = 0;
+    uint64_t last_trace_overflow_ = 0;
 };
 
 } // namespace artb

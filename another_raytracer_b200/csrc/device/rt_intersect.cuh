@@ -197,31 +197,38 @@ ARTB_HD bool medium_interval(const SceneView& s, uint32_t first, uint32_t count,
     return medium_interval_general(s, first, count, world, t1, t2);
 }
 
+// log(u) behind a call: the compiler must not start the (long) double-precision logarithm before the float test
+// below has decided that it is needed
+ARTB_HD_NOINLINE double medium_log(double u) { return log(u); }
+
 ARTB_HD bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, double t_min, double t_max,
                       const MediumXi& xi, double& t)
 {
     // constant_medium.h:44-69
     const uint32_t first = uint32_t(p.g[1]), count = uint32_t(p.g[2]);
+    const double u = xi.get(uint32_t(p.g[3]));
+    // explicit-xi table: NaN marks "the reference drew nothing here", i.e. its interval was already empty
+    // because a closer surface had been found first — then this medium cannot be the closest hit either
+    if (!(u == u)) return false;
+    // Most queries end with "scattered beyond the interval". Decide the clear cases with a float logarithm:
+    // |log(u) - __logf(float(u))| <= 1e-6 (1 + |log u|) (2^-21.4 absolute / 3 ulp, plus the rounding of u), so a
+    // lower bound of hit_distance that already exceeds the interval is a certain miss; everything else takes the
+    // reference's double-precision expression below.
+    const float lf = fast_logf(float(u));
+    const double hit_distance_lo = -p.g[0] * double(-lf - 1e-6f * (1.f - lf));
+    const double ray_length = length(world.d);
+    // ... and before the boundary is even intersected: the clamped interval lies within [max(t_min, 0), t_max], and
+    // subtraction and multiplication round monotonically, so (t_max - max(t_min, 0)) * |d| bounds it from above
+    if (hit_distance_lo > (t_max - (t_min > 0 ? t_min : 0.0)) * ray_length) return false;
     double t1, t2;
     if (!medium_interval(s, first, count, world, t1, t2)) return false;
     if (t1 < t_min) t1 = t_min;
     if (t2 > t_max) t2 = t_max;
     if (t1 >= t2) return false;
     if (t1 < 0) t1 = 0;
-    const double ray_length = length(world.d);
     const double distance_inside_boundary = (t2 - t1) * ray_length;
-    const double u = xi.get(uint32_t(p.g[3]));
-    // explicit-xi table: NaN marks "the reference drew nothing here", i.e. its interval was already empty
-    // because a closer surface had been found first — then this medium cannot be the closest hit either
-    if (!(u == u)) return false;
-    // Most queries end here with "scattered beyond the interval". Decide the clear cases with a float logarithm:
-    // |log(u) - __logf(float(u))| <= 1e-6 (1 + |log u|) (2^-21.4 absolute / 3 ulp, plus the rounding of u), so a
-    // lower bound of hit_distance that already exceeds the interval is a certain miss; everything else takes the
-    // reference's double-precision expression below.
-    const float lf = fast_logf(float(u));
-    const double hit_distance_lo = -p.g[0] * double(-lf - 1e-6f * (1.f - lf));
     if (hit_distance_lo > distance_inside_boundary) return false;
-    const double hit_distance = p.g[0] * log(u);
+    const double hit_distance = p.g[0] * medium_log(u);
     if (hit_distance > distance_inside_boundary) return false;
     t = t1 + hit_distance / ray_length;
     return true;
@@ -431,15 +438,20 @@ ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Trav
     const bool want_prims = tv.alive && tv.pg.y != 0u;
     const uint32_t m_prims = warp_ballot(wm, want_prims);
     if (ARTB_PRIM_VOTE_DEN * pop_count(m_prims) >= ARTB_PRIM_VOTE_NUM * pop_count(m_alive)) {
-        if (want_prims) {
-            do {
+        // every lane of the warp takes this branch (the vote is uniform): one candidate per lane and round, with a
+        // re-convergence point after each, so that the many exits of the primitive tests meet again
+        bool more = want_prims;
+        while (warp_ballot(wm, more) != 0u) {
+            if (more) {
                 const int bit = find_msb(tv.pg.y);
                 tv.pg.y &= ~(1u << bit);
                 ARTB_STAT(stats, prims);
                 test_surface(s, tv.pg.x + uint32_t(bit), ray, t_min, tv.best);
-            } while (tv.pg.y);
-            tv.t_best_f = d2f_ru(tv.best.t);
+                more = tv.pg.y != 0u;
+            }
+            warp_sync_mask(wm);
         }
+        if (want_prims) tv.t_best_f = d2f_ru(tv.best.t);
     } else if (tv.alive && !want_prims) {
         // here ng holds at least one internal child: enter the one the ray meets first
         const uint32_t hits = tv.ng.y;
@@ -496,36 +508,39 @@ ARTB_HD void test_global_media(const SceneView& s, const DRay& ray, const BoxRay
 }
 
 // ---- two-phase closest hit: FP32 candidate collection, then double-precision confirmation -------------------------
-// Phase 1 (k_traverse) walks the tree with the float ray only and records every primitive whose quantised leaf box
-// the ray enters within [t_min, t_max]: no primitive data, no doubles, no pruning by hits — so the walk is a pure
-// FP32 / shared-memory loop with few registers, and since nothing a lane finds changes what it visits next, lanes can
-// be refilled one by one. (Measured on the reference's scenes: 1.1-1.3x the node visits of the pruned walk.)
-// Phase 2 (k_confirm) runs the reference's double-precision test on exactly those candidates. The box tests are
-// conservative, so every primitive the reference could report is among the candidates, and the closest-hit rule
-// (minimum t, ties to the larger depth-first id) does not depend on the order: the result is the same as the
-// one-phase walk's. A ray with more than ARTB_CAND_CAP candidates is flagged and traced by the one-phase walk.
-#define ARTB_CAND_CAP 31
-#define ARTB_CAND_OVERFLOW 0x80000000u
-struct ARTB_ALIGN(16) CandRec { uint32_t count; uint32_t ids[ARTB_CAND_CAP]; };      // 128 B; count bit 31: overflow
-
-struct Collector { uint2 ng; int sp; uint32_t count; };
+// Phase 1 (k_traverse) walks the tree with the float ray only and emits a (ray, primitive) PAIR for every primitive
+// whose quantised leaf box the ray enters within [t_min, t_max]: no primitive data, no doubles, no pruning by hits —
+// so the walk is a pure FP32 / shared-memory loop with few registers, and since nothing a lane finds changes what it
+// visits next, lanes can be refilled one by one. (Measured on the reference's scenes: 1.1-1.3x the node visits of the
+// pruned walk.) Phase 2 (k_pairs) runs the reference's double-precision test on exactly those pairs, one pair per
+// thread, and merges the results per ray. The box tests are conservative, so every primitive the reference could
+// report is among the candidates, and the closest-hit rule (minimum t, ties to the larger depth-first id) does not
+// depend on the order: the result is the same as the one-phase walk's.
+struct Collector { uint2 ng; int sp; };
 
 ARTB_HD void collect_begin(Collector& c, bool has_tree)
 {
     c.ng = make_uint2(0u, has_tree ? 0x80000000u : 0u);
     c.sp = 0;
-    c.count = 0;
 }
 
-// one node visit; false when the walk has ended (tree exhausted, or the candidate list is full: count gets the flag)
-template <class NodePtr>
-ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
-                          uint32_t* ids, TraversalStats* stats)
+// One node visit, in two parts so that a warp can re-converge between them (k_traverse):
+//   collect_pop   false when the walk has ended (nothing pending and the stack is empty)
+//   collect_node  enters the nearest pending child; the primitives of its leaf children that were hit are
+//                 prims[prim_base + b] for every set bit b of prim_mask (possibly none)
+ARTB_HD bool collect_pop(Collector& c, const uint2* stack)
 {
     if (c.ng.y <= 0x00ffffffu) {
         if (c.sp == 0) return false;
         c.ng = stack[--c.sp];
     }
+    return true;
+}
+
+template <class NodePtr>
+ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
+                          uint32_t& prim_base, uint32_t& prim_mask, TraversalStats* stats)
+{
     const uint32_t hits = c.ng.y;
     const int bit = find_msb(hits);
     c.ng.y &= ~(1u << bit);
@@ -538,32 +553,26 @@ ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float 
     const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f);
     c.ng.x = n1.x;
     c.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
-    uint32_t m = hitmask & 0x00ffffffu;
-    while (m) {
-        const int b = find_msb(m);
-        m &= ~(1u << b);
-        if (c.count >= ARTB_CAND_CAP) { c.count = ARTB_CAND_CAP | ARTB_CAND_OVERFLOW; return false; }
-        ids[c.count++] = n1.y + uint32_t(b);
-    }
+    prim_base = n1.y;
+    prim_mask = hitmask & 0x00ffffffu;
+}
+
+template <class NodePtr>
+ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
+                          uint32_t& prim_base, uint32_t& prim_mask, TraversalStats* stats)
+{
+    prim_mask = 0u;
+    if (!collect_pop(c, stack)) return false;
+    collect_node(nodes, br, t_min_f, t_max_f, c, stack, prim_base, prim_mask, stats);
     return true;
 }
 
-// phase 2 for one ray: global surfaces, the candidates, then the media (order as in closest_hit below)
-ARTB_HD ClosestHit confirm_candidates(const SceneView& s, const DRay& ray, double t_min, double t_max, const MediumXi& xi,
-                                      uint32_t count, const uint32_t* ids, TraversalStats* stats)
+// The merge rule of phase 2, i.e. what hittable_list::hit / bvh_node::hit do by narrowing t_max (hittable_list.cpp:11-15,
+// bvh.cpp:48-49): a candidate replaces the best iff it is closer, or equally close and later in the reference's
+// depth-first order.
+ARTB_HD bool hit_is_better(double t, uint32_t dfs, double best_t, int32_t best_prim, uint32_t best_dfs)
 {
-    Traversal tv;
-    trav_begin(tv, t_max, false);
-    test_global_surfaces(s, ray, t_min, tv, stats);
-    for (uint32_t k = 0; k < count; ++k) {
-        ARTB_STAT(stats, prims);
-        test_surface(s, ids[k], ray, t_min, tv.best);
-    }
-    if (s.n_global_media) {
-        const BoxRay br = make_box_ray(ray);
-        test_global_media(s, ray, br, t_min, d2f_rd(t_min), xi, tv.best, stats);
-    }
-    return tv.best;
+    return t < best_t || (t == best_t && (best_prim < 0 || dfs > best_dfs));
 }
 
 // one ray per lane from start to end (k_trace_batch, hostsim); k_extend drives the same pieces itself so that it
@@ -584,7 +593,9 @@ ARTB_HD ClosestHit closest_hit(const SceneView& s, NodePtr nodes, const DRay& ra
     return tv.best;
 }
 
-// both phases for one ray (hostsim; the kernels run the phases in separate launches)
+// both phases for one ray (hostsim; the kernels run the phases in separate launches): global surfaces, the pairs,
+// then the media — the order k_finish / closest_hit use
+#define ARTB_HOSTSIM_MAX_PAIRS 4096
 template <class NodePtr>
 ARTB_HD ClosestHit closest_hit_two_phase(const SceneView& s, NodePtr nodes, const DRay& ray, double t_min, double t_max,
                                          const MediumXi& xi, TraversalStats* stats = nullptr)
@@ -593,10 +604,33 @@ ARTB_HD ClosestHit closest_hit_two_phase(const SceneView& s, NodePtr nodes, cons
     Collector c;
     collect_begin(c, s.n_world_prims > s.n_global_prims);
     uint2 stack[ARTB_STACK_DEPTH];
-    uint32_t ids[ARTB_CAND_CAP];
-    while (collect_step(nodes, br, d2f_rd(t_min), d2f_ru(t_max), c, stack, ids, stats)) { }
-    if (c.count & ARTB_CAND_OVERFLOW) return closest_hit(s, nodes, ray, t_min, t_max, xi, stats);
-    return confirm_candidates(s, ray, t_min, t_max, xi, c.count, ids, stats);
+    uint32_t ids[ARTB_HOSTSIM_MAX_PAIRS];
+    uint32_t count = 0, base = 0, mask = 0;
+    while (collect_step(nodes, br, d2f_rd(t_min), d2f_ru(t_max), c, stack, base, mask, stats)) {
+        while (mask) {
+            const int b = find_msb(mask);
+            mask &= ~(1u << b);
+            if (count == ARTB_HOSTSIM_MAX_PAIRS) return closest_hit(s, nodes, ray, t_min, t_max, xi, stats);
+            ids[count++] = base + uint32_t(b);
+        }
+    }
+    ClosestHit best;
+    best.t = t_max; best.prim = -1; best.dfs = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+        ARTB_STAT(stats, prims);
+        const FlatPrim& p = s.prims[ids[k]];
+        if (p.type == PRIM_MEDIUM) continue;
+        double t;
+        const bool ok = p.xform ? surface_t(p, to_object_space(s, p.xform, ray), t_min, t_max, t) : surface_t(p, ray, t_min, t_max, t);
+        if (ok && hit_is_better(t, p.dfs_id, best.t, best.prim, best.dfs)) { best.t = t; best.prim = int32_t(ids[k]); best.dfs = p.dfs_id; }
+    }
+    const uint32_t n_surf = s.n_global_prims - s.n_global_media;
+    for (uint32_t i = 0; i < n_surf; ++i) {
+        ARTB_STAT(stats, prims);
+        test_surface(s, i, ray, t_min, best);
+    }
+    if (s.n_global_media) test_global_media(s, ray, br, t_min, d2f_rd(t_min), xi, best, stats);
+    return best;
 }
 
 } // namespace artb

@@ -191,6 +191,11 @@ class Context:
         _check(self._lib.artb_trace_batch(self._h, rays.ctypes.data, n, t_min, t_max, xi_ptr, out.ctypes.data), self._h)
         return out
 
+    @property
+    def trace_overflow_rays(self) -> int:
+        """rays of the last trace_batch that took the one-phase overflow pass (0: all went through the pair kernels)"""
+        return int(self._lib.artb_trace_overflow_rays(self._h))
+
     def trace_batch_device(self, rays_ptr: int, n: int, hits_ptr: int, t_min: float = 0.001, t_max: float = float("inf"),
                            xi_ptr: int | None = None) -> float:
         ms = C.c_float(0)

@@ -302,7 +302,9 @@ def run_cuda_arm(args, wl):
                         "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                         "extend_share_of_step": ext_ms / max(sum(s["elapsed_ms"] for s in stats), 1e-9),
                         "traverse_ms_per_launch": sum(s["traverse_ms"] for s in stats) / max(ext_launches, 1),
-                        "confirm_ms_per_launch": sum(s["confirm_ms"] for s in stats) / max(ext_launches, 1)}
+                        "pairs_ms_per_launch": sum(s["pairs_ms"] for s in stats) / max(ext_launches, 1),
+                        "finish_ms_per_launch": sum(s["finish_ms"] for s in stats) / max(ext_launches, 1),
+                        "overflow_rays": int(sum(s["overflow_rays"] for s in stats))}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_reference_run(wl, os.cpu_count() or 1)

@@ -117,6 +117,9 @@ int artb_trace_batch(artb_ctx* ctx, const double* rays, uint64_t n, double t_min
 /* same on DEVICE pointers; *kernel_ms (optional) receives the CUDA-event time of the traversal kernel */
 int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, double t_min, double t_max,
                             const double* medium_xi_dev, artb_hit* hits_dev, float* kernel_ms);
+/* how many rays of the last artb_trace_batch* call took the one-phase overflow pass instead of the pair kernels
+ * (0 for the reference's scenes; the tests assert it so that parity is known to cover the kernels the renderer runs) */
+uint64_t artb_trace_overflow_rays(const artb_ctx* ctx);
 
 /* ---- engine::run (engine.h:30-54) ------------------------------------------------------------------ */
 typedef struct artb_camera {            /* camera::camera arguments, camera.h:8-17 */
@@ -150,7 +153,8 @@ typedef struct artb_stats {
     double extend_ms; uint64_t extend_launches;
     uint64_t pixels_active, pixels_converged;
     uint64_t h2d_bytes, d2h_bytes;
-    double traverse_ms, confirm_ms;     /* profile=1: the two kernels of the closest-hit stage (extend_ms = whole stage) */
+    double traverse_ms, pairs_ms, finish_ms;   /* profile=1: the kernels of the closest-hit stage (extend_ms = whole stage) */
+    uint64_t overflow_rays;             /* rays traced by the one-phase overflow pass */
 } artb_stats;
 
 /* rgb8_out: W*H*3 bytes, row 0 = top, RGB (the layout engine::run writes). accum_out (optional):

@@ -37,6 +37,7 @@ def test_closest_hit_matches_reference(artb, gpu_ctx, scenes, alias):
     assert scene.info["n_media"] == int(g["n_media"])
     gpu_ctx.upload(scene)
     out = gpu_ctx.trace_batch(g["rays"], 0.001, float("inf"), g["xi"] if int(g["n_media"]) else None)
+    assert gpu_ctx.trace_overflow_rays == 0, "golden rays must go through k_traverse / k_pairs / k_finish, not the overflow pass"
 
     ref_hit = g["hit"].astype(bool)
     assert np.array_equal(out["hit"].astype(bool), ref_hit), "hit / miss decisions differ"

@@ -7,7 +7,7 @@ for lib in another_raytracer_b200/libartb*.so; do
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
-    print(f\"{d['value']:8.1f} Msamples/s  step {d['ms_per_step']:7.2f} ms  extend {r['avg_launch_ms']:.4f} ms/launch  share {r['extend_share_of_step']:.3f}  checksum {d['image_checksum']}  trav {r.get('traverse_ms_per_launch',0):.4f} conf {r.get('confirm_ms_per_launch',0):.4f}\")
+    print(f\"{d['value']:8.1f} Msamples/s  step {d['ms_per_step']:7.2f} ms  extend {r['avg_launch_ms']:.4f} ms/launch  share {r['extend_share_of_step']:.3f}  checksum {d['image_checksum']}  trav {r.get('traverse_ms_per_launch',0):.4f} pairs {r.get('pairs_ms_per_launch',0):.4f} fin {r.get('finish_ms_per_launch',0):.4f} ovf {r.get('overflow_rays',0)}\")
 except Exception as e:
     print('FAILED', e)
 "

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-source-line summary of an ncu report captured with --import-source on (kernels built with -lineinfo).
 
-usage: ncu_lines.py report.ncu-rep [top_n]
+usage: ncu_lines.py report.ncu-rep [top_n] [kernel regex] [inst: sort by instructions instead of stall samples]
 Prints, for every file the kernel's SASS maps to, the lines with the most warp-stall samples together with the
 warp instructions executed there and the mean number of active threads per instruction (lane efficiency).
 """
@@ -14,7 +14,8 @@ from collections import defaultdict
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+    kern = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+    txt = subprocess.run(["ncu", "-i", rep, *kern, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                          capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     cur_file, header = None, None
@@ -51,7 +52,7 @@ def main():
                     pass
     print(f"total samples {tot_s}  warp instructions {tot_i}  lane efficiency {tot_t / max(tot_i, 1):.2f}/32")
     print(f"{'file:line':28s} {'samp%':>6s} {'inst%':>6s} {'lanes':>5s}  top stalls / source")
-    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if len(sys.argv) > 4 and sys.argv[4] == 'inst' else 0])[:top]:
         st = sorted(stalls[(f, l)].items(), key=lambda kv: -kv[1])[:3]
         sts = " ".join(f"{k[6:]}={v}" for k, v in st if v)
         print(f"{f + ':' + str(l):28s} {100 * a[0] / max(tot_s, 1):6.2f} {100 * a[1] / max(tot_i, 1):6.2f} "
