@@ -281,6 +281,9 @@ __device__ __forceinline__ void merge_hit(PathHit* h, unsigned long long cur_lo,
 #ifndef ARTB_TRAVERSE_THREADS
 #define ARTB_TRAVERSE_THREADS 1024
 #endif
+#ifndef ARTB_TRAVERSE_BLOCKS
+#define ARTB_TRAVERSE_BLOCKS 1        // resident blocks per SM (registers: 65536 / threads / blocks)
+#endif
 #ifndef ARTB_REFILL_MIN_IDLE
 #define ARTB_REFILL_MIN_IDLE 8        // a warp stops to fetch new rays once this many of its lanes are idle
 #endif
@@ -290,7 +293,7 @@ extern __shared__ uint4 smem_nodes[];
 // scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
 // Otherwise nodes are read through L1/L2.
 template <bool kShared, bool kBatch>
-__global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared ? 1 : 3)
+__global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared ? ARTB_TRAVERSE_BLOCKS : 3)
 k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
     __shared__ uint32_t s_pairs;      // pairs this block has appended to its region
@@ -393,7 +396,7 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 #define ARTB_PAIRS_THREADS 256
 #endif
 #ifndef ARTB_PAIRS_BLOCKS
-#define ARTB_PAIRS_BLOCKS 3
+#define ARTB_PAIRS_BLOCKS 4
 #endif
 #define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory
 template <bool kBatch>
@@ -844,7 +847,7 @@ struct Renderer::Impl {
     void set_pair_buffer(const SceneView& view, TraceIO& io, uint2* pairs, size_t capacity, uint32_t* region_count) const
     {
         io.pb.pairs = pairs; io.pb.region_count = region_count;
-        io.pb.n_regions = nodes_fit_shared(view) ? uint32_t(sm_count) : uint32_t(sm_count) * 6u;
+        io.pb.n_regions = nodes_fit_shared(view) ? uint32_t(sm_count) * ARTB_TRAVERSE_BLOCKS : uint32_t(sm_count) * 6u;
         io.pb.region_cap = uint32_t(std::min<size_t>(capacity / io.pb.n_regions, 0x7fffffffu));
     }
     template <bool kBatch>
@@ -920,6 +923,7 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     w.q_shade = dev_alloc<uint32_t>(impl_->pool_allocs, size_t(pool_paths) * MAT_COUNT);
     w.q_overflow = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
     w.pair_capacity = size_t(pool_paths) * ARTB_PAIRS_PER_RAY;
+    if (const char* e = getenv("ARTB_PAIR_CAPACITY")) w.pair_capacity = std::max<size_t>(size_t(atoll(e)), 1);   // test knob: forces the overflow pass
     w.pairs = dev_alloc<uint2>(impl_->pool_allocs, w.pair_capacity);
     w.region_count = dev_alloc<uint32_t>(impl_->pool_allocs, ARTB_MAX_REGIONS);
     w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
@@ -1002,7 +1006,8 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
     try {
         const uint64_t kChunk = 1u << 22;                         // rays per pass
         const uint64_t cap = std::min<uint64_t>(n, kChunk);
-        const size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
+        size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
+        if (const char* e = getenv("ARTB_PAIR_CAPACITY")) pair_capacity = std::max<size_t>(size_t(atoll(e)), 1);
         PathHit* hits = dev_alloc<PathHit>(bag, cap);
         uint2* pairs = dev_alloc<uint2>(bag, pair_capacity);
         uint32_t* region_count = dev_alloc<uint32_t>(bag, ARTB_MAX_REGIONS);
