@@ -27,6 +27,16 @@ namespace artb {
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
     throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// Path state: ONE 128-byte line per pool slot — ray (64 B) | aux (32 B) | hit (16 B) | pad — so that a kernel that
+// needs the ray, the path's bookkeeping and its hit record touches exactly one aligned line (four sectors) per path.
+// (As three separate arrays the 16- and 32-byte records dragged their neighbours' sectors along on every random
+// access: ncu showed 320 B of DRAM reads per ray in k_finish for 116 B of payload.)
+#define ARTB_PATH_STRIDE 128
+template <class T>
+struct Strided {
+    char* base; uint32_t stride;
+    __host__ __device__ __forceinline__ T* at(uint32_t i) const { return reinterpret_cast<T*>(base + size_t(i) * stride); }
+};
 struct __align__(16) PathRay { double o[3], d[3], tm, pad; };                       // 64 B
 struct __align__(16) PathAux { float thr[3]; uint32_t pixel, sample, rng_block, depth, pad; };   // 32 B
 struct __align__(16) PathHit { double t; int32_t prim; uint32_t dfs; };             // 16 B: the best hit so far
@@ -56,9 +66,9 @@ struct WaveCounters {
 #define ARTB_PAIRS_PER_RAY 8         // capacity of the pair buffer per pool slot (mean over a wave; measured 3-4)
 #endif
 struct WaveBuffers {
-    PathRay* rays;
-    PathAux* aux;
-    PathHit* hits;
+    Strided<PathRay> rays;            // views into the pool of 128-byte path records
+    Strided<PathAux> aux;
+    Strided<PathHit> hits;
     uint32_t* q_extend[2];
     uint32_t* q_regen[2];
     uint32_t* q_shade;                // MAT_COUNT queues of `pool` entries, back to back
@@ -107,9 +117,9 @@ __device__ __forceinline__ uint32_t multi_queue_reserve(int key, uint32_t* count
     return base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
 }
 
-__device__ __forceinline__ DRay load_ray(const PathRay* rays, uint32_t slot)
+__device__ __forceinline__ DRay load_ray(const PathRay* ray)
 {
-    const double2* p = reinterpret_cast<const double2*>(rays + slot);
+    const double2* p = reinterpret_cast<const double2*>(ray);
     const double2 a = p[0], b = p[1], c = p[2], d = p[3];
     DRay r;
     r.o = mk3(a.x, a.y, b.x);
@@ -118,25 +128,25 @@ __device__ __forceinline__ DRay load_ray(const PathRay* rays, uint32_t slot)
     return r;
 }
 
-__device__ __forceinline__ void store_ray(PathRay* rays, uint32_t slot, const DRay& r)
+__device__ __forceinline__ void store_ray(PathRay* ray, const DRay& r)
 {
-    double2* p = reinterpret_cast<double2*>(rays + slot);
+    double2* p = reinterpret_cast<double2*>(ray);
     p[0] = make_double2(r.o.x, r.o.y);
     p[1] = make_double2(r.o.z, r.d.x);
     p[2] = make_double2(r.d.y, r.d.z);
     p[3] = make_double2(r.tm, 0.0);
 }
 
-__device__ __forceinline__ void load_aux(const PathAux* aux, uint32_t slot, PathAux& a)
+__device__ __forceinline__ void load_aux(const PathAux* aux, PathAux& a)
 {
-    *reinterpret_cast<uint4*>(&a) = *reinterpret_cast<const uint4*>(aux + slot);
-    *(reinterpret_cast<uint4*>(&a) + 1) = *(reinterpret_cast<const uint4*>(aux + slot) + 1);
+    *reinterpret_cast<uint4*>(&a) = *reinterpret_cast<const uint4*>(aux);
+    *(reinterpret_cast<uint4*>(&a) + 1) = *(reinterpret_cast<const uint4*>(aux) + 1);
 }
 
-__device__ __forceinline__ void store_aux(PathAux* aux, uint32_t slot, const PathAux& a)
+__device__ __forceinline__ void store_aux(PathAux* aux, const PathAux& a)
 {
-    *reinterpret_cast<uint4*>(aux + slot) = *reinterpret_cast<const uint4*>(&a);
-    *(reinterpret_cast<uint4*>(aux + slot) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
+    *reinterpret_cast<uint4*>(aux) = *reinterpret_cast<const uint4*>(&a);
+    *(reinterpret_cast<uint4*>(aux) + 1) = *(reinterpret_cast<const uint4*>(&a) + 1);
 }
 
 __device__ __forceinline__ void add_radiance(const RoundParams& rp, uint32_t pixel, float r, float g, float b)
@@ -209,15 +219,15 @@ struct PairBuf {
 struct TraceIO {
     const uint32_t* n_ptr;            // number of rays of this launch (device memory)
     const uint32_t* list;             // ray ids (path slots); nullptr: 0..n-1
-    PathHit* hits;                    // one record per ray id: the best hit so far; prim == ARTB_HIT_OVERFLOW: some of the
+    Strided<PathHit> hits;            // one record per ray id: the best hit so far; prim == ARTB_HIT_OVERFLOW: some of the
                                       // ray's pairs did not fit, the overflow pass traces it
     PairBuf pb;
     uint32_t* cursor_traverse;
     uint32_t* q_overflow;
     uint32_t* n_overflow;
     double t_min, t_max;
-    const PathRay* rays;              // wave mode: the path pool
-    const PathAux* aux;
+    Strided<PathRay> rays;            // wave mode: the path pool
+    Strided<PathAux> aux;
     const double* batch_rays;         // batch mode: n * 7 doubles
     const double* batch_xi;           // batch mode: n * n_media explicit medium draws, or nullptr
     HitRecordOut* batch_out;
@@ -232,7 +242,7 @@ __device__ __forceinline__ DRay trace_io_ray(const TraceIO& io, uint32_t id)
         r.o = ld3(p); r.d = ld3(p + 3); r.tm = p[6];
         return r;
     }
-    return load_ray(io.rays, id);
+    return load_ray(io.rays.at(id));
 }
 
 __device__ __forceinline__ PathHit load_hit(const PathHit* h)
@@ -347,7 +357,7 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
                     const DRay r = trace_io_ray<kBatch>(io, id);
                     br = make_box_ray(make_trav_ray(r));
                     collect_begin(col, has_tree);
-                    store_hit(io.hits + id, io.t_max, -1, 0u);
+                    store_hit(io.hits.at(id), io.t_max, -1, 0u);
                     active = true;
                     spilled = false;
                 }
@@ -357,7 +367,7 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
         }
         uint32_t prim_base = 0, prim_mask = 0;
         if (active && !collect_pop(col, stack)) {
-            if (spilled) mark_overflow(io.hits + id);
+            if (spilled) mark_overflow(io.hits.at(id));
             active = false;
         }
         warp_sync();
@@ -453,7 +463,7 @@ k_pairs(TraceIO io, SceneView s)
             unsigned long long cur_lo = 0, cur_hi = 0;
             if (i < n_live) {
                 pq = tile[i];
-                peek_hit(io.hits + pq.x, cur_lo, cur_hi);
+                peek_hit(io.hits.at(pq.x), cur_lo, cur_hi);
                 const FlatPrim& p = s.prims[pq.y];
                 dfs = p.dfs_id;
                 DRay q = trace_io_ray<kBatch>(io, pq.x);
@@ -461,7 +471,7 @@ k_pairs(TraceIO io, SceneView s)
                 ok = surface_t(p, q, io.t_min, io.t_max, t);
             }
             warp_sync();
-            if (ok && t == t) merge_hit(io.hits + pq.x, cur_lo, cur_hi, t, pq.y, dfs);
+            if (ok && t == t) merge_hit(io.hits.at(pq.x), cur_lo, cur_hi, t, pq.y, dfs);
             warp_sync();
         }
         __syncthreads();
@@ -501,14 +511,14 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
         PathAux a;
         a.thr[0] = a.thr[1] = a.thr[2] = 0.f; a.pixel = a.sample = a.rng_block = a.depth = a.pad = 0;
         if (valid) {
-            ph = load_hit(io.hits + id);
+            ph = load_hit(io.hits.at(id));
             r = trace_io_ray<kBatch>(io, id);
-            if (!kBatch) load_aux(io.aux, id, a);
+            if (!kBatch) load_aux(io.aux.at(id), a);
         }
         if (next_idx < n) {
-            prefetch_l1(io.hits + next_id);
+            prefetch_l1(io.hits.at(next_id));
             if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
-            else { prefetch_l1(io.rays + next_id); prefetch_l1(io.aux + next_id); }
+            else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
         }
         const bool overflow = ph.prim == ARTB_HIT_OVERFLOW;
         queue_push(io.q_overflow, io.n_overflow, overflow, id, lane);
@@ -549,7 +559,7 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
                 add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
                              a.thr[2] * float(s.background[2]));
             } else {
-                store_hit(w.hits + id, best.t, best.prim, best.dfs);
+                store_hit(w.hits.at(id), best.t, best.prim, best.dfs);
                 key = int(s.prim_mat_type[best.prim]);
             }
         }
@@ -599,9 +609,9 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
         const uint32_t slot = valid ? list[base + lane] : 0u;
         int key = -1;
         if (valid) {
-            const DRay r = load_ray(w.rays, slot);
+            const DRay r = load_ray(w.rays.at(slot));
             PathAux a;
-            load_aux(w.aux, slot, a);
+            load_aux(w.aux.at(slot), a);
             MediumXi xi;
             xi.row = nullptr; xi.seed = rp.seed; xi.stream = rp.stream;
             xi.path_lo = a.pixel; xi.path_hi = a.sample; xi.bounce = a.depth;
@@ -611,7 +621,7 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
                 add_radiance(rp, a.pixel, a.thr[0] * float(s.background[0]), a.thr[1] * float(s.background[1]),
                              a.thr[2] * float(s.background[2]));
             } else {
-                store_hit(w.hits + slot, h.t, h.prim, h.dfs);
+                store_hit(w.hits.at(slot), h.t, h.prim, h.dfs);
                 key = int(s.materials[s.prims[h.prim].material].type);
             }
         }
@@ -681,20 +691,20 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
                     const double u = (px + g.next_double()) / (rp.width - 1);
                     const double v = ((rp.height - 1 - py) + g.next_double()) / (rp.height - 1);
                     const DRay r = camera_ray(rp.cam, u, v, g);
-                    store_ray(w.rays, slot, r);
+                    store_ray(w.rays.at(slot), r);
                     PathAux a;
                     a.thr[0] = a.thr[1] = a.thr[2] = 1.f;
                     a.pixel = pixel; a.sample = sample; a.rng_block = g.c2; a.depth = 0; a.pad = 0;
-                    store_aux(w.aux, slot, a);
+                    store_aux(w.aux.at(slot), a);
                 }
             }
         } else if (valid) {
-            const DRay r = load_ray(w.rays, slot);
+            const DRay r = load_ray(w.rays.at(slot));
             PathAux a;
-            load_aux(w.aux, slot, a);
-            const PathHit ph = load_hit(w.hits + slot);
+            load_aux(w.aux.at(slot), a);
+            const PathHit ph = load_hit(w.hits.at(slot));
             if (next_valid && next_m != Q_REGEN) {
-                prefetch_l1(w.rays + next_slot); prefetch_l1(w.aux + next_slot); prefetch_l1(w.hits + next_slot);
+                prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
             }
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
@@ -709,10 +719,10 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
                 const bool ok = material_scatter(s, mat, r, h, g, att, sc);
                 if (ok && a.depth + 1u < uint32_t(rp.max_depth)) {
                     key = 0;
-                    store_ray(w.rays, slot, sc);
+                    store_ray(w.rays.at(slot), sc);
                     a.thr[0] *= float(att.x); a.thr[1] *= float(att.y); a.thr[2] *= float(att.z);
                     a.depth += 1; a.rng_block = g.c2;
-                    store_aux(w.aux, slot, a);
+                    store_aux(w.aux.at(slot), a);
                 } else {
                     add_radiance(rp, a.pixel, 0.f, 0.f, 0.f);   // absorbed / depth limit: a black sample (engine.h:451-452, 462-463)
                 }
@@ -905,6 +915,7 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("ARTB_MAX_SHARED_NODES")) impl_->max_shared_nodes = size_t(atoll(e));   // tuning knob (bytes)
+    if (const char* e = getenv("ARTB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoll(e)));
     cudaStream_t st;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     stream_ = st;
@@ -913,9 +924,10 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     pool_paths = (pool_paths + 31u) & ~31u;
     WaveBuffers& w = impl_->wb;
     w.pool = pool_paths;
-    w.rays = dev_alloc<PathRay>(impl_->pool_allocs, pool_paths);
-    w.aux = dev_alloc<PathAux>(impl_->pool_allocs, pool_paths);
-    w.hits = dev_alloc<PathHit>(impl_->pool_allocs, pool_paths);
+    char* recs = dev_alloc<char>(impl_->pool_allocs, size_t(pool_paths) * ARTB_PATH_STRIDE);
+    w.rays = { recs, ARTB_PATH_STRIDE };
+    w.aux = { recs + sizeof(PathRay), ARTB_PATH_STRIDE };
+    w.hits = { recs + sizeof(PathRay) + sizeof(PathAux), ARTB_PATH_STRIDE };
     for (int k = 0; k < 2; ++k) {
         w.q_extend[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
         w.q_regen[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
@@ -1021,7 +1033,7 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
             CUDA_CHECK(cudaMemcpyAsync(ctr, init, sizeof(init), cudaMemcpyHostToDevice, st));
             CUDA_CHECK(cudaStreamSynchronize(st));               // `init` lives on this stack frame
             TraceIO io{};
-            io.n_ptr = ctr; io.list = nullptr; io.hits = hits;
+            io.n_ptr = ctr; io.list = nullptr; io.hits = { reinterpret_cast<char*>(hits), uint32_t(sizeof(PathHit)) };
             impl_->set_pair_buffer(view_, io, pairs, pair_capacity, region_count);
             io.cursor_traverse = ctr + 1; io.q_overflow = overflow; io.n_overflow = ctr + 3;
             io.t_min = t_min; io.t_max = t_max;
