@@ -19,6 +19,7 @@ SYMBOLS = [
     "artb_scene_build", "artb_scene_free", "artb_scene_get_info", "artb_scene_dump_graph", "artb_scene_get_flat",
     "artb_upload_scene", "artb_upload_flat",
     "artb_trace_batch", "artb_trace_batch_device", "artb_trace_overflow_rays",
+    "artb_build_bvh_device", "artb_last_bvh_build",
     "artb_render", "artb_render_device", "artb_resolve_device", "artb_stream",
     "artb_save_png", "artb_host_rng_reset", "artb_host_rng_next",
 ]
@@ -34,7 +35,7 @@ class Config(C.Structure):
 
 class SceneOptions(C.Structure):
     _fields_ = [("mesh_as_soup", C.c_int32), ("heightfield_side", C.c_int32), ("max_leaf_prims", C.c_int32),
-                ("reserved", C.c_int32), ("assets_root", C.c_char_p)]
+                ("device_bvh", C.c_int32), ("assets_root", C.c_char_p)]
 
 
 class SceneInfo(C.Structure):
@@ -80,6 +81,11 @@ class RenderParams(C.Structure):
                 ("accumulate", C.c_int32), ("profile", C.c_int32)]
 
 
+class BvhStats(C.Structure):
+    _fields_ = [("build_ms", C.c_double), ("n_prims", C.c_uint32), ("n_nodes", C.c_uint32), ("depth", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("elapsed_ms", C.c_double), ("samples", C.c_uint64), ("rays", C.c_uint64), ("waves", C.c_uint64),
                 ("launches", C.c_uint64), ("extend_ms", C.c_double), ("extend_launches", C.c_uint64),
@@ -119,6 +125,10 @@ def load() -> C.CDLL:
     lib.artb_upload_flat.argtypes = [vp, C.POINTER(FlatSceneView)]
     lib.artb_trace_batch.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp]
     lib.artb_trace_batch_device.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp, C.POINTER(C.c_float)]
+    lib.artb_build_bvh_device.argtypes = [vp, C.c_int32, C.POINTER(BvhStats)]
+    lib.artb_build_bvh_device.restype = C.c_int
+    lib.artb_last_bvh_build.argtypes = [vp, C.POINTER(BvhStats)]
+    lib.artb_last_bvh_build.restype = C.c_int
     lib.artb_trace_overflow_rays.argtypes = [vp]
     lib.artb_trace_overflow_rays.restype = C.c_uint64
     lib.artb_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), vp, vp, vp, C.POINTER(Stats)]

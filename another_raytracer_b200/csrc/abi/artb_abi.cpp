@@ -166,6 +166,7 @@ int artb_scene_build(int32_t alias, const artb_scene_options* opt, artb_scene** 
         s->rng_next = random_double();
         FlattenOptions fo;
         if (opt && opt->max_leaf_prims > 0) fo.max_leaf_prims = opt->max_leaf_prims;
+        if (opt && opt->device_bvh) fo.device_bvh = true;
         s->flat = flatten(s->host.objects, s->host.background, fo);
         *out = s.release();
         return ARTB_OK;
@@ -335,6 +336,31 @@ int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, d
         if (kernel_ms) *kernel_ms = ms;
         return ARTB_OK;
     });
+}
+
+static void to_bvh_stats(const BvhBuildStats& b, artb_bvh_stats* out)
+{
+    if (!out) return;
+    out->build_ms = b.total_ms; out->n_prims = b.n_prims; out->n_nodes = b.n_nodes; out->depth = b.depth; out->reserved = 0;
+}
+
+int artb_build_bvh_device(artb_ctx* ctx, int32_t max_leaf_prims, artb_bvh_stats* stats)
+{
+    if (!ctx) return fail(ctx, ARTB_E_INVALID, "null argument");
+    if (!ctx->renderer->has_scene()) return fail(ctx, ARTB_E_EMPTY_SCENE, "Invalid input scene!");
+    return guarded(ctx, [&]() -> int {
+        BvhBuildStats b;
+        ctx->renderer->build_bvh_device(max_leaf_prims > 0 ? max_leaf_prims : 1, &b);
+        to_bvh_stats(b, stats);
+        return ARTB_OK;
+    });
+}
+
+int artb_last_bvh_build(const artb_ctx* ctx, artb_bvh_stats* stats)
+{
+    if (!ctx || !stats) return ARTB_E_INVALID;
+    to_bvh_stats(ctx->renderer->last_build(), stats);
+    return ARTB_OK;
 }
 
 uint64_t artb_trace_overflow_rays(const artb_ctx* ctx)

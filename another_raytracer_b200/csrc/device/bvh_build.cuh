@@ -22,17 +22,12 @@
 #define ARTB_BVH_BUILD_CUH
 
 #include "flat_scene.h"
+#include "renderer.h"
 #include "rt_math.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 
 namespace artb {
-
-struct BvhBuildStats {
-    double total_ms = 0;              // CUDA-event time of the whole build
-    uint32_t n_prims = 0, n_nodes = 0;
-    int depth = 0;                    // levels of 8-wide nodes
-};
 
 namespace bvhb {
 

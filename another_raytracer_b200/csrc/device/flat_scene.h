@@ -112,6 +112,9 @@ struct FlatPerlin {       // perlin.h:56-61
 // Code path a primitive takes in the double-precision test: k_pairs sorts each tile of pairs by it so that the lanes of
 // a warp run the same test (sphere / moving sphere / rect / triangle, each without or with a transform chain).
 #define ARTB_PRIM_CLASSES 8
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
 inline uint32_t prim_class_of(uint32_t type, uint32_t xform)
 {
     const uint32_t path = type == PRIM_SPHERE ? 0u : type == PRIM_MSPHERE ? 1u : type == PRIM_TRIANGLE ? 3u : 2u;

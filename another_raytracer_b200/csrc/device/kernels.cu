@@ -16,6 +16,7 @@
 // no kernel waits on another one and the queue counters are reset inside the kernels (see WaveCounters).
 #include "renderer.h"
 #include "rt_shade.cuh"
+#include "bvh_build.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -968,6 +969,7 @@ void Renderer::upload(const FlatScene& fs)
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (void* p : impl_->scene_allocs) cudaFree(p);
     impl_->scene_allocs.clear();
+    last_build_ = BvhBuildStats{};
     if (fs.bvh_depth > ARTB_MAX_BVH8_DEPTH)
         throw std::runtime_error("scene BVH is deeper than the device traversal stack");
     uint64_t bytes = 0;
@@ -1002,6 +1004,9 @@ void Renderer::upload(const FlatScene& fs)
     view_ = v;
     scene_bytes_ = bytes;
     has_scene_ = true;
+    // a flat scene that arrives without a tree (FlattenOptions::device_bvh, or a foreign host that has none) gets
+    // one built here, on the device
+    if (fs.nodes.empty() && fs.n_world_prims > fs.n_global_prims) build_bvh_device(fs.device_bvh_leaf_prims, &last_build_);
 }
 
 float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_min, double t_max, const double* xi_dev,
@@ -1098,6 +1103,112 @@ void Renderer::resolve_device(const float* accum_dev, const uint32_t* count_dev,
     k_resolve<<<(n_pixels + 255) / 256, 256, 0, st>>>(accum_dev, count_dev, n_pixels, fixed_spp, rgb_dev);
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+// ---- device BVH build (bvh_build.cuh) ------------------------------------------------------------------------------
+__global__ void k_prim_tables(const FlatPrim* prims, const FlatMaterial* materials, uint32_t n_materials, uint32_t n, uint8_t* prim_class,
+                              uint8_t* prim_mat_type)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FlatPrim& p = prims[i];
+    prim_class[i] = uint8_t(prim_class_of(p.type, p.xform));
+    prim_mat_type[i] = p.material < n_materials ? uint8_t(materials[p.material].type) : uint8_t(0);
+}
+
+void Renderer::build_bvh_device(int max_leaf_prims, BvhBuildStats* stats)
+{
+    if (!has_scene_) throw std::runtime_error("build_bvh_device: no scene uploaded");
+    if (max_leaf_prims < 1) max_leaf_prims = 1;
+    if (max_leaf_prims > ARTB_MAX_LEAF_PRIMS) throw std::runtime_error("build_bvh_device: max_leaf_prims exceeds ARTB_MAX_LEAF_PRIMS");
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    BvhBuildStats S;
+    const uint32_t first = view_.n_global_prims;
+    const uint32_t n = view_.n_world_prims - view_.n_global_prims;
+    S.n_prims = n;
+    if (n == 0) { if (stats) *stats = S; return; }
+    using namespace bvhb;
+    std::vector<void*> bag;
+    FlatNode8* nodes_tmp = nullptr;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    try {
+        Arrays A{};
+        const size_t n_bin = 2 * size_t(n);
+        A.box_lo = dev_alloc<float4>(bag, n); A.box_hi = dev_alloc<float4>(bag, n);
+        A.node_lo = dev_alloc<float4>(bag, n_bin); A.node_hi = dev_alloc<float4>(bag, n_bin);
+        A.left = dev_alloc<int>(bag, n); A.right = dev_alloc<int>(bag, n); A.parent = dev_alloc<int>(bag, n_bin);
+        A.first = dev_alloc<int>(bag, n); A.last = dev_alloc<int>(bag, n);
+        A.flag = dev_alloc<unsigned int>(bag, n);
+        A.keys = dev_alloc<unsigned long long>(bag, n); A.keys_sorted = dev_alloc<unsigned long long>(bag, n);
+        A.idx = dev_alloc<uint32_t>(bag, n); A.idx_sorted = dev_alloc<uint32_t>(bag, n);
+        A.bounds = dev_alloc<int>(bag, 6);
+        A.perm = dev_alloc<uint32_t>(bag, n);
+        A.queue[0] = dev_alloc<uint2>(bag, n); A.queue[1] = dev_alloc<uint2>(bag, n);
+        A.counters = dev_alloc<uint32_t>(bag, 4);
+        const uint32_t node_capacity = n;                       // wide nodes <= binary internal nodes + 1
+        nodes_tmp = dev_alloc<FlatNode8>(bag, node_capacity);
+        FlatPrim* prims_tmp = dev_alloc<FlatPrim>(bag, n);
+        int* d_error = dev_alloc<int>(bag, 1);
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, A.keys, A.keys_sorted, A.idx, A.idx_sorted, int(n), 0, 63, st);
+        void* sort_tmp = dev_alloc<char>(bag, sort_bytes);
+        FlatPrim* prims = const_cast<FlatPrim*>(view_.prims) + first;
+        const unsigned B = 256, G = (n + B - 1) / B;
+
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        CUDA_CHECK(cudaMemsetAsync(d_error, 0, sizeof(int), st));
+        k_bvh_init<<<G, B, 0, st>>>(A, n);
+        k_bvh_boxes<<<G, B, 0, st>>>(prims, n, view_.xform_ops, view_.xforms, A);
+        k_bvh_morton<<<G, B, 0, st>>>(n, A);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, A.keys, A.keys_sorted, A.idx, A.idx_sorted, int(n), 0, 63, st));
+        if (n > 1) k_bvh_karras<<<G, B, 0, st>>>(int(n), A);
+        else CUDA_CHECK(cudaMemsetAsync(A.parent, 0xff, sizeof(int), st));      // a single leaf: node (n-1)+0 = 0, no parent
+        k_bvh_refit<<<G, B, 0, st>>>(int(n), A);
+        // level by level; the host only reads the length of the next level's queue
+        uint32_t n_jobs = 1;
+        int level = 0;
+        while (n_jobs) {
+            if (++S.depth > ARTB_MAX_BVH8_DEPTH) throw std::runtime_error("build_bvh_device: tree deeper than the traversal stack allows");
+            k_bvh_next_level<<<1, 1, 0, st>>>(A);
+            k_bvh_collapse<<<(n_jobs + 127) / 128, 128, 0, st>>>(int(n), int(n_jobs), level, max_leaf_prims, A, nodes_tmp, node_capacity, d_error);
+            uint32_t ctr[4];
+            CUDA_CHECK(cudaMemcpyAsync(ctr, A.counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            n_jobs = ctr[2];
+            S.n_nodes = ctr[0];
+            level ^= 1;
+        }
+        int err = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&err, d_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (err) throw std::runtime_error("build_bvh_device: quantisation / capacity error " + std::to_string(err));
+        // primitives into leaf order, then the per-primitive tables and the final node array
+        k_bvh_permute<<<(n * 6 + B - 1) / B, B, 0, st>>>(prims, prims_tmp, A.perm, n);
+        CUDA_CHECK(cudaMemcpyAsync(prims, prims_tmp, size_t(n) * sizeof(FlatPrim), cudaMemcpyDeviceToDevice, st));
+        k_bvh_offset_prim_base<<<(S.n_nodes + B - 1) / B, B, 0, st>>>(nodes_tmp, S.n_nodes, first);
+        FlatNode8* nodes = dev_alloc<FlatNode8>(impl_->scene_allocs, S.n_nodes);
+        CUDA_CHECK(cudaMemcpyAsync(nodes, nodes_tmp, size_t(S.n_nodes) * sizeof(FlatNode8), cudaMemcpyDeviceToDevice, st));
+        k_prim_tables<<<(view_.n_prims + B - 1) / B, B, 0, st>>>(view_.prims, view_.materials, view_.n_materials, view_.n_prims,
+                                                                 const_cast<uint8_t*>(view_.prim_class), const_cast<uint8_t*>(view_.prim_mat_type));
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaGetLastError());
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        S.total_ms = ms;
+        view_.nodes = nodes;                 // the previous node array stays in scene_allocs until the next upload
+        view_.n_nodes = S.n_nodes;
+    } catch (...) {
+        for (void* p : bag) cudaFree(p);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        throw;
+    }
+    for (void* p : bag) cudaFree(p);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) *stats = S;
 }
 
 void Renderer::render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,

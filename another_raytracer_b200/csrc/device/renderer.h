@@ -43,6 +43,12 @@ struct RenderStats {
     unsigned long long pixels_active = 0, pixels_converged = 0;
 };
 
+struct BvhBuildStats {
+    double total_ms = 0;              // CUDA-event time of the whole device build
+    uint32_t n_prims = 0, n_nodes = 0;
+    int depth = 0;                    // levels of 8-wide nodes
+};
+
 class Renderer {
 public:
     Renderer(int device, uint32_t pool_paths);
@@ -55,6 +61,11 @@ public:
     uint32_t n_media() const { return view_.n_media; }
     uint64_t scene_bytes() const { return scene_bytes_; }
     uint64_t last_trace_overflow() const { return last_trace_overflow_; }   // rays of the last trace_batch that took the one-phase pass
+
+    // (Re)build the 8-wide BVH of the uploaded scene ON THE DEVICE (bvh_build.cuh): replaces the node array and puts the
+    // tree primitives into the new leaf order. upload() calls it by itself for a flat scene that carries no nodes.
+    void build_bvh_device(int max_leaf_prims, BvhBuildStats* stats);
+    const BvhBuildStats& last_build() const { return last_build_; }
 
     // parity hook: closest hit for explicit rays. rays = n*7 doubles (o, d, time), xi = n*n_media or null.
     void trace_batch(const double* rays_host, uint64_t n, double t_min, double t_max, const double* xi_host,
@@ -85,6 +96,7 @@ private:
     SceneView view_{};
     uint64_t scene_bytes_ = 0;
     uint64_t last_trace_overflow_ = 0;
+    BvhBuildStats last_build_{};
 };
 
 } // namespace artb

@@ -634,6 +634,13 @@ private:
         const int n = int(world_items.size());
         if (n == 0) return;
         if (opt.max_leaf_prims > ARTB_MAX_LEAF_PRIMS) throw std::logic_error("flatten: max_leaf_prims exceeds ARTB_MAX_LEAF_PRIMS");
+        if (opt.device_bvh) {
+            // no host tree: the primitives go out in walk order and Renderer::upload builds the tree on the GPU
+            for (const Item& it : world_items) out.prims.push_back(it.prim);
+            out.device_bvh_leaf_prims = std::max(opt.max_leaf_prims, 1);
+            out.bvh_depth = 0;
+            return;
+        }
         order.resize(size_t(n));
         for (int i = 0; i < n; ++i) order[size_t(i)] = i;
         tnodes.reserve(size_t(2 * n));

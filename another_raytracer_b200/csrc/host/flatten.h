@@ -44,6 +44,7 @@ struct FlatScene {
     double background[3] = {0, 0, 0};
     double world_lo[3] = {0, 0, 0}, world_hi[3] = {0, 0, 0};
     int bvh_depth = 0;                    // levels of 8-wide nodes
+    int device_bvh_leaf_prims = 1;        // leaf size for the device builder when `nodes` is empty (FlattenOptions::device_bvh)
 };
 
 struct FlattenOptions {
@@ -53,6 +54,7 @@ struct FlattenOptions {
     int sah_bins = 16;
     double traversal_cost = 1.0;
     double intersect_cost = 1.5;
+    bool device_bvh = false;              // skip the host SAH build: leave `nodes` empty, Renderer::upload builds the tree on the GPU
 };
 
 FlatScene flatten(const hittable_list& world, const color& background, const FlattenOptions& opt = FlattenOptions());

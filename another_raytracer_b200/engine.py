@@ -72,9 +72,11 @@ class Scene:
 
     @classmethod
     def build(cls, alias, mesh_as_soup: bool = False, heightfield_side: int = 0, max_leaf_prims: int = 0,
-              assets_root: str | None = None) -> "Scene":
+              assets_root: str | None = None, device_bvh: bool = False) -> "Scene":
+        """device_bvh=True skips the host SAH build: the flat scene carries no nodes and Context.upload builds the
+        8-wide tree on the GPU (csrc/device/bvh_build.cuh)."""
         lib = _abi.load()
-        opt = _abi.SceneOptions(int(mesh_as_soup), int(heightfield_side), int(max_leaf_prims), 0,
+        opt = _abi.SceneOptions(int(mesh_as_soup), int(heightfield_side), int(max_leaf_prims), int(device_bvh),
                                 assets_root.encode() if assets_root else None)
         h = C.c_void_p()
         _check(lib.artb_scene_build(int(alias), C.byref(opt), C.byref(h)))
@@ -190,6 +192,23 @@ class Context:
             xi_ptr = medium_xi.ctypes.data
         _check(self._lib.artb_trace_batch(self._h, rays.ctypes.data, n, t_min, t_max, xi_ptr, out.ctypes.data), self._h)
         return out
+
+    def build_bvh_device(self, max_leaf_prims: int = 1) -> dict:
+        """artb_build_bvh_device: rebuild the tree of the uploaded scene on the GPU; returns build_ms / n_nodes / depth"""
+        st = _abi.BvhStats()
+        _check(self._lib.artb_build_bvh_device(self._h, max_leaf_prims, C.byref(st)), self._h)
+        return {"build_ms": st.build_ms, "n_prims": st.n_prims, "n_nodes": st.n_nodes, "depth": st.depth}
+
+    @staticmethod
+    def last_global_prims(scene: "Scene") -> int:
+        """number of global primitives (tested for every ray, not in the tree) of a scene"""
+        return int(scene.flat_view().n_global_prims)
+
+    @property
+    def last_bvh_build(self) -> dict:
+        st = _abi.BvhStats()
+        self._lib.artb_last_bvh_build(self._h, C.byref(st))
+        return {"build_ms": st.build_ms, "n_prims": st.n_prims, "n_nodes": st.n_nodes, "depth": st.depth}
 
     @property
     def trace_overflow_rays(self) -> int:

@@ -45,6 +45,9 @@ WORKLOADS = {
     "random": dict(alias=1, width=400, height=225, name="rtiow_random_spheres_400x225", full_spp=10),
     "cow": dict(alias=10, width=1920, height=1080, name="cow_obj_1920x1080", full_spp=256),
     "dino": dict(alias=11, width=1920, height=1080, name="dino_obj_1920x1080", full_spp=256),
+    # BASELINE.json configs[4]: 1 M-triangle height field at 4K; the tree is built on the GPU (bvh_build.cuh)
+    "heightfield": dict(alias=12, width=3840, height=2160, name="heightfield_1M_triangles_3840x2160", full_spp=64,
+                        scene_kwargs=dict(mesh_as_soup=True, device_bvh=True)),
 }
 
 
@@ -206,9 +209,10 @@ def run_cuda_arm(args, wl):
         dist.init_process_group("nccl", device_id=dev)
 
     W, H, alias, S = wl["width"], wl["height"], wl["alias"], args.spp_per_step
-    scene = A.Scene.build(alias)
+    scene = A.Scene.build(alias, **wl.get("scene_kwargs", {}))
     ctx = A.Context(local, args.pool)
     ctx.upload(scene)
+    bvh_build = ctx.last_bvh_build
     cam = scene.camera(W, H)
     step_accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     total_accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
@@ -316,7 +320,8 @@ def run_cuda_arm(args, wl):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "scene_alias": alias, "width": W, "height": H, "max_depth": 50,
                        "spp_per_step": S, "full_config_spp": wl["full_spp"], "partition": f"samples x{world}", "pool_paths": args.pool,
-                       "seed": args.seed, "l2": "256 MiB flush buffer written between timed steps; path pool > L2"},
+                       "seed": args.seed, "l2": "256 MiB flush buffer written between timed steps; path pool > L2",
+                       "device_bvh_build_ms": bvh_build["build_ms"] if bvh_build["n_nodes"] else None},
             "mrays_per_sec": rays / (dev_ms_max * 1e-3) / 1e6, "rays_per_sample": rays / max(samples, 1),
             "wall_ms_per_step": wall_ms_max / max(args.steps, 1),
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

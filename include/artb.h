@@ -54,7 +54,7 @@ typedef struct artb_scene_options {
     int32_t mesh_as_soup;      /* aliases 9-11: flatten the .obj as one triangle_soup (no per-triangle objects) */
     int32_t heightfield_side;  /* alias 12: vertices per side (0 = 708 -> 999 698 triangles) */
     int32_t max_leaf_prims;    /* device BVH leaf size (0 = default) */
-    int32_t reserved;
+    int32_t device_bvh;        /* 1: skip the host SAH build; artb_upload_scene builds the 8-wide tree on the GPU */
     const char* assets_root;   /* NULL: $ARTB_ASSETS or <repo>/assets */
 } artb_scene_options;
 
@@ -117,6 +117,18 @@ int artb_trace_batch(artb_ctx* ctx, const double* rays, uint64_t n, double t_min
 /* same on DEVICE pointers; *kernel_ms (optional) receives the CUDA-event time of the traversal kernel */
 int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, double t_min, double t_max,
                             const double* medium_xi_dev, artb_hit* hits_dev, float* kernel_ms);
+/* (Re)build the 8-wide BVH of the uploaded scene ON THE GPU (replaces the bvh_node constructor, bvh.cpp:3-42, for the
+ * tree the kernels traverse; results do not depend on the tree). max_leaf_prims: 1..3 (0 = 1). */
+typedef struct artb_bvh_stats {
+    double build_ms;                    /* CUDA-event time of the device build */
+    uint32_t n_prims, n_nodes;
+    int32_t depth;                      /* levels of 8-wide nodes */
+    int32_t reserved;
+} artb_bvh_stats;
+int artb_build_bvh_device(artb_ctx* ctx, int32_t max_leaf_prims, artb_bvh_stats* stats);
+/* stats of the build artb_upload_scene / artb_upload_flat ran by itself (all zero if the scene came with a tree) */
+int artb_last_bvh_build(const artb_ctx* ctx, artb_bvh_stats* stats);
+
 /* how many rays of the last artb_trace_batch* call took the one-phase overflow pass instead of the pair kernels
  * (0 for the reference's scenes; the tests assert it so that parity is known to cover the kernels the renderer runs) */
 uint64_t artb_trace_overflow_rays(const artb_ctx* ctx);
