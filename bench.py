@@ -51,6 +51,18 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the closest-hit kernels from the committed ncu --set full capture (profiles/traffic.json,
+    written by tools/ncu_summary.py traffic <report>); None when that file is missing."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.loads(p.read_text())
+        return {"bytes_per_launch": int(sum(v for k, v in t["kernels"].items() if k in ("k_traverse", "k_pairs", "k_finish"))),
+                "per_kernel": t["kernels"], "source": t.get("source")}
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -300,8 +312,12 @@ def run_cuda_arm(args, wl):
         roofline = None
         if b_ray and ext_ms > 0:
             achieved = b_ray * rank0_rays / (ext_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            tr = ncu_traffic()
+            roofline = {"bound": "hbm", "kernel": "closest-hit stage = k_traverse + k_pairs + k_finish (+ k_extend overflow pass)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": tr["bytes_per_launch"] if tr else None,
+                        "traffic_per_kernel": tr["per_kernel"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                        "peak_source": peak_src,
                         "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rank0_rays / max(ext_launches, 1),
                         "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
                         "extend_share_of_step": ext_ms / max(sum(s["elapsed_ms"] for s in stats), 1e-9),

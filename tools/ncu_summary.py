@@ -61,5 +61,23 @@ def report(path):
             print(f"{key:90s} [{rows[1][i]}] {[r[i] for r in rows[2:]]}")
 
 
+def traffic(path):
+    """profiles/traffic.json: mean dram__bytes_read.sum + dram__bytes_write.sum per launch of every captured kernel"""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    kcol, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = re.sub(r"^void\s+|<.*$|\(.*$", "", r[kcol]).split("::")[-1]
+        agg[name].append(float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]])
+    res = {"source": f"{path}: ncu --set full --clock-control none, mean over the captured launches (steady-state waves of bench.py)",
+           "kernels": {k: int(sum(v) / len(v)) for k, v in agg.items()}}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
