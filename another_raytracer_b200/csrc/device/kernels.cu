@@ -118,6 +118,32 @@ __device__ __forceinline__ uint32_t multi_queue_reserve(int key, uint32_t* count
     return base + uint32_t(__popc(peers & ((1u << lane) - 1u)));
 }
 
+// The same append split in two, so that the round trip of the atomic is not waited for: `reserve` elects the leaders
+// and issues their atomicAdd; `commit` — called one loop iteration later — reads the result and writes the entry.
+struct PendingAppend {
+    uint32_t* queue;        // nullptr: nothing pending
+    uint32_t value, rank, base_raw;
+    int leader;
+};
+
+__device__ __forceinline__ void append_commit(PendingAppend& p)
+{
+    const uint32_t base = __shfl_sync(0xffffffffu, p.base_raw, p.leader);
+    if (p.queue) p.queue[base + p.rank] = p.value;
+    p.queue = nullptr;
+}
+
+__device__ __forceinline__ void append_reserve(PendingAppend& p, int key, uint32_t* counter, uint32_t* queue, uint32_t value, int lane)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    p.leader = __ffs(peers) - 1;
+    p.rank = uint32_t(__popc(peers & ((1u << lane) - 1u)));
+    p.base_raw = 0;
+    if (key >= 0 && lane == p.leader) p.base_raw = atomicAdd(counter, uint32_t(__popc(peers)));
+    p.queue = key >= 0 ? queue : nullptr;
+    p.value = value;
+}
+
 __device__ __forceinline__ DRay load_ray(const PathRay* ray)
 {
     const double2* p = reinterpret_cast<const double2*>(ray);
@@ -479,6 +505,9 @@ k_pairs(TraceIO io, SceneView s)
     }
 }
 
+#ifndef ARTB_FINISH_DEFER
+#define ARTB_FINISH_DEFER 0           // deferred queue appends cost k_finish more in spills than the hidden latency gains
+#endif
 #ifndef ARTB_FINISH_THREADS
 #define ARTB_FINISH_THREADS 128
 #endif
@@ -499,6 +528,8 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
     uint32_t id = 0;
     if (base + uint32_t(lane) < n) id = io.list ? io.list[base + lane] : base + uint32_t(lane);
+    PendingAppend pend;
+    pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
@@ -565,14 +596,21 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
             }
         }
         if (!kBatch) {
+#if ARTB_FINISH_DEFER
+            append_commit(pend);             // the previous iteration's entries: their atomics have long returned
+            append_reserve(pend, key, &c->n_out[cur][key < 0 ? 0 : key],
+                           key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key < 0 ? 0 : key) * w.pool, id, lane);
+#else
             const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
             if (key >= 0) {
                 uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
                 q[pos] = id;
             }
+#endif
         }
         id = next_id;
     }
+    if (!kBatch) append_commit(pend);
 }
 
 // The one-phase walk: closest_hit() per ray, results appended to the same queues. all = 0: the rays k_finish found
@@ -648,10 +686,10 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
         c->cursor[0] = c->cursor[1] = c->cursor[2] = 0;
         c->n_overflow = 0;
     }
-    uint32_t start[Q_OUT_COUNT + 1];
+    uint32_t start[Q_OUT_COUNT + 1], qn[Q_OUT_COUNT];
     start[0] = 0;
 #pragma unroll
-    for (int m = 0; m < Q_OUT_COUNT; ++m) start[m + 1] = start[m] + ((c->n_out[cur][m] + 31u) >> 5);
+    for (int m = 0; m < Q_OUT_COUNT; ++m) { qn[m] = c->n_out[cur][m]; start[m + 1] = start[m] + ((qn[m] + 31u) >> 5); }
     const unsigned long long issued = c->issued, total = c->total;
     const uint32_t n_list = c->n_list;
     const int lane = threadIdx.x & 31;
@@ -659,10 +697,11 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
     // which queue a warp index belongs to, the lane's entry in it and the slot stored there
     auto locate = [&](uint32_t wi, int& m, uint32_t& i, bool& valid) -> uint32_t {
         m = 0;
+        uint32_t first = 0, count = qn[0];
 #pragma unroll
-        for (int k = 1; k < Q_OUT_COUNT; ++k) if (wi >= start[k]) m = k;
-        i = (wi - start[m]) * 32u + uint32_t(lane);
-        valid = wi < start[Q_OUT_COUNT] && i < c->n_out[cur][m];
+        for (int k = 1; k < Q_OUT_COUNT; ++k) if (wi >= start[k]) { m = k; first = start[k]; count = qn[k]; }
+        i = (wi - first) * 32u + uint32_t(lane);
+        valid = wi < start[Q_OUT_COUNT] && i < count;
         if (!valid) return 0u;
         return m == Q_REGEN ? w.q_regen[cur][i] : w.q_shade[size_t(m) * w.pool + i];
     };
@@ -671,6 +710,8 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
     uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int m = 0; uint32_t i = 0; bool valid = false;
     uint32_t slot = locate(wi, m, i, valid);
+    PendingAppend pend;
+    pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
         int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
         const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
@@ -729,10 +770,12 @@ __global__ void __launch_bounds__(128) k_shade(WaveBuffers w, SceneView s, Round
                 }
             }
         }
-        const uint32_t pos = multi_queue_reserve(key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1], lane);
-        if (key >= 0) (key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1])[pos] = slot;
+        append_commit(pend);                 // the previous iteration's entries: their atomics have long returned
+        append_reserve(pend, key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1],
+                       key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1], slot, lane);
         m = next_m; i = next_i; valid = next_valid; slot = next_slot;
     }
+    append_commit(pend);
 }
 
 // adaptive variance mask: keep the pixels of the current list whose luminance mean is not yet settled.
