@@ -135,6 +135,8 @@ struct SceneView {
     const FlatPerlin* perlins;
     uint32_t n_prims, n_world_prims, n_global_prims, n_nodes, n_media, n_xforms, n_materials, n_textures;
     uint32_t n_global_media;          // media among the global primitives (tested after the traversal)
+    uint32_t one_bits;                // 0x3f800000 as a RUNTIME value: the node test wants it in a register next to immediate
+                                      // PRMT selectors; as a literal ptxas re-materialises it before every PRMT (rt_intersect.cuh)
     double background[3];
 };
 

@@ -398,7 +398,7 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
             active = false;
         }
         warp_sync();
-        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, nullptr);
+        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, s.one_bits, nullptr);
         warp_sync();
         // append this step's pairs: positions from a warp-wide scan + one shared-memory atomic per warp
         const uint32_t cnt = uint32_t(__popc(prim_mask));
@@ -1042,6 +1042,7 @@ void Renderer::upload(const FlatScene& fs)
     v.n_textures = uint32_t(fs.textures.size());
     v.n_global_prims = fs.n_global_prims;
     v.n_global_media = fs.n_global_media;
+    v.one_bits = 0x3f800000u;
     for (int k = 0; k < 3; ++k) v.background[k] = fs.background[k];
     CUDA_CHECK(cudaStreamSynchronize(st));
     view_ = v;

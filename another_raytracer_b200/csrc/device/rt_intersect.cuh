@@ -339,8 +339,30 @@ ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t
 // node. All of it is below pad = (|c| + |B| + 2|A|) * 2^-21, which is SUBTRACTED from near planes and ADDED to far
 // planes: the interval only grows. 2|A|*2^-21 is 1/32 of a quantisation cell, so the loosening is invisible next to
 // the quantisation itself.
+// child J of a group of four: byte J of each plane word -> mantissa of 1.0f (selector bytes: 00 | q_J | 80 | 3f)
+template <int J>
+ARTB_HD void node8_child(uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4, uint32_t fy4, uint32_t fz4, const float* A,
+                         const float* Bn, const float* Bf, float t_min, float t_best, uint32_t child_bits4, uint32_t bit_index4,
+                         uint32_t one, uint32_t& hitmask)
+{
+    constexpr uint32_t kSel = 0x7604u | (uint32_t(J) << 4);
+    const float tnx = fmaf(as_float(byte_perm_sel<kSel>(nx4, one)), A[0], Bn[0]);
+    const float tny = fmaf(as_float(byte_perm_sel<kSel>(ny4, one)), A[1], Bn[1]);
+    const float tnz = fmaf(as_float(byte_perm_sel<kSel>(nz4, one)), A[2], Bn[2]);
+    const float tfx = fmaf(as_float(byte_perm_sel<kSel>(fx4, one)), A[0], Bf[0]);
+    const float tfy = fmaf(as_float(byte_perm_sel<kSel>(fy4, one)), A[1], Bf[1]);
+    const float tfz = fmaf(as_float(byte_perm_sel<kSel>(fz4, one)), A[2], Bf[2]);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_best));
+    if (tn <= tf) {
+        const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
+        const uint32_t index = (bit_index4 >> (8 * J)) & 0xffu;
+        hitmask |= bits << index;
+    }
+}
+
 ARTB_HD uint32_t node8_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const BoxRay& r,
-                            float t_min, float t_best)
+                            float t_min, float t_best, uint32_t one /* SceneView::one_bits */)
 {
     float A[3], Bn[3], Bf[3];
     const float p[3] = { as_float(n0.x), as_float(n0.y), as_float(n0.z) };
@@ -368,23 +390,10 @@ ARTB_HD uint32_t node8_hits(const uint4 n0, const uint4 n1, const uint4 n2, cons
         const uint32_t nx4 = px ? qlox : qhix, fx4 = px ? qhix : qlox;
         const uint32_t ny4 = py ? qloy : qhiy, fy4 = py ? qhiy : qloy;
         const uint32_t nz4 = pz ? qloz : qhiz, fz4 = pz ? qhiz : qloz;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t sel = 0x7604u | (uint32_t(j) << 4);                       // bytes: 00 | q_j | 80 | 3f
-            const float tnx = fmaf(as_float(byte_perm(nx4, 0x3f800000u, sel)), A[0], Bn[0]);
-            const float tny = fmaf(as_float(byte_perm(ny4, 0x3f800000u, sel)), A[1], Bn[1]);
-            const float tnz = fmaf(as_float(byte_perm(nz4, 0x3f800000u, sel)), A[2], Bn[2]);
-            const float tfx = fmaf(as_float(byte_perm(fx4, 0x3f800000u, sel)), A[0], Bf[0]);
-            const float tfy = fmaf(as_float(byte_perm(fy4, 0x3f800000u, sel)), A[1], Bf[1]);
-            const float tfz = fmaf(as_float(byte_perm(fz4, 0x3f800000u, sel)), A[2], Bf[2]);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_min));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_best));
-            if (tn <= tf) {
-                const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
-                const uint32_t index = (bit_index4 >> (8 * j)) & 0xffu;
-                hitmask |= bits << index;
-            }
-        }
+        node8_child<0>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
+        node8_child<1>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
+        node8_child<2>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
+        node8_child<3>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
     }
     return hitmask;
 }
@@ -463,7 +472,7 @@ ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Trav
         const uint4* q = reinterpret_cast<const uint4*>(nodes + (tv.ng.x + rel));
         const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
         ARTB_STAT(stats, nodes);
-        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f);
+        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f, s.one_bits);
         tv.ng.x = n1.x;
         tv.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
         tv.pg.x = n1.y;
@@ -539,7 +548,7 @@ ARTB_HD bool collect_pop(Collector& c, const uint2* stack)
 
 template <class NodePtr>
 ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
-                          uint32_t& prim_base, uint32_t& prim_mask, TraversalStats* stats)
+                          uint32_t& prim_base, uint32_t& prim_mask, uint32_t one_bits, TraversalStats* stats)
 {
     const uint32_t hits = c.ng.y;
     const int bit = find_msb(hits);
@@ -550,7 +559,7 @@ ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float 
     const uint4* q = reinterpret_cast<const uint4*>(nodes + (c.ng.x + rel));
     const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
     ARTB_STAT(stats, nodes);
-    const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f);
+    const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f, one_bits);
     c.ng.x = n1.x;
     c.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
     prim_base = n1.y;
@@ -559,11 +568,11 @@ ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float 
 
 template <class NodePtr>
 ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
-                          uint32_t& prim_base, uint32_t& prim_mask, TraversalStats* stats)
+                          uint32_t& prim_base, uint32_t& prim_mask, uint32_t one_bits, TraversalStats* stats)
 {
     prim_mask = 0u;
     if (!collect_pop(c, stack)) return false;
-    collect_node(nodes, br, t_min_f, t_max_f, c, stack, prim_base, prim_mask, stats);
+    collect_node(nodes, br, t_min_f, t_max_f, c, stack, prim_base, prim_mask, one_bits, stats);
     return true;
 }
 
@@ -606,7 +615,7 @@ ARTB_HD ClosestHit closest_hit_two_phase(const SceneView& s, NodePtr nodes, cons
     uint2 stack[ARTB_STACK_DEPTH];
     uint32_t ids[ARTB_HOSTSIM_MAX_PAIRS];
     uint32_t count = 0, base = 0, mask = 0;
-    while (collect_step(nodes, br, d2f_rd(t_min), d2f_ru(t_max), c, stack, base, mask, stats)) {
+    while (collect_step(nodes, br, d2f_rd(t_min), d2f_ru(t_max), c, stack, base, mask, s.one_bits, stats)) {
         while (mask) {
             const int b = find_msb(mask);
             mask &= ~(1u << b);

@@ -37,6 +37,7 @@ int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, doub
     s.n_nodes = f->n_nodes; s.n_media = f->n_media; s.n_xforms = f->n_xforms;
     s.n_materials = f->n_materials; s.n_textures = f->n_textures;
     s.n_global_media = 0;
+    s.one_bits = 0x3f800000u;
     for (uint32_t i = 0; i < s.n_global_prims; ++i) s.n_global_media += s.prims[i].type == PRIM_MEDIUM ? 1u : 0u;
     for (int k = 0; k < 3; ++k) s.background[k] = f->background[k];
 
