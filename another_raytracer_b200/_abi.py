@@ -26,7 +26,7 @@ SYMBOLS = [
 
 ARTB_OK = 0
 ARTB_E_INVALID, ARTB_E_NO_DEVICE, ARTB_E_CUDA, ARTB_E_SCENE, ARTB_E_EMPTY_SCENE, ARTB_E_ADAPTIVE_SIZE = -1, -2, -3, -4, -5, -6
-MODE_FIXED, MODE_VARIANCE_MASK = 0, 1
+MODE_FIXED, MODE_VARIANCE_MASK, MODE_ADAPTIVE_SQUARES = 0, 1, 2
 
 
 class Config(C.Structure):

@@ -102,7 +102,7 @@ RenderParams to_params(const artb_render_params& p)
     r.tile_size = p.tile_size > 0 ? p.tile_size : 32;
     r.tile_parts = p.tile_parts > 1 ? p.tile_parts : 1;
     r.tile_part = p.tile_part;
-    r.adaptive = p.mode == ARTB_MODE_VARIANCE_MASK ? 1 : 0;
+    r.adaptive = p.mode == ARTB_MODE_VARIANCE_MASK ? 1 : (p.mode == ARTB_MODE_ADAPTIVE_SQUARES ? 2 : 0);
     r.adaptive_min_spp = p.adaptive_min_spp > 0 ? p.adaptive_min_spp : 16;
     r.adaptive_batch_spp = p.adaptive_batch_spp > 0 ? p.adaptive_batch_spp : 8;
     r.adaptive_threshold = p.adaptive_threshold > 0 ? p.adaptive_threshold : 0.02;
@@ -281,7 +281,7 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
             if (p.type == PRIM_MEDIUM && (p.g[1] < fs.n_world_prims || p.g[1] + p.g[2] > double(fs.prims.size())))
                 throw std::logic_error("flat scene: medium boundary range out of bounds");
         }
-        if (fs.n_world_prims > fs.n_global_prims && fs.nodes.empty()) throw std::logic_error("flat scene: BVH primitives without nodes");
+        // BVH primitives without nodes: allowed — Renderer::upload then builds the tree on the device (bvh_build.cuh)
         if (fs.bvh_depth < 0 || fs.bvh_depth > 24) throw std::logic_error("flat scene: bvh_depth out of range");
         for (const FlatNode8& n : fs.nodes) {
             uint32_t inner = 0;
@@ -374,6 +374,8 @@ int artb_render(artb_ctx* ctx, const artb_camera* cam, const artb_render_params*
     const int rc = check_render_args(ctx, cam, p);
     if (rc != ARTB_OK) return rc;
     if (!rgb8_out) return fail(ctx, ARTB_E_INVALID, "null output image");
+    if (p->mode == ARTB_MODE_ADAPTIVE_SQUARES && (p->width % 12 != 0 || p->height % 12 != 0))      // engine.h:182-183
+        return fail(ctx, ARTB_E_ADAPTIVE_SIZE, "for adaptive strategy image size should perfectly fit big square size for now!!");
     return guarded(ctx, [&]() -> int {
         RenderStats s;
         ctx->renderer->render_host(make_camera(*cam), to_params(*p), rgb8_out, accum_out, count_out, &s);

@@ -17,6 +17,7 @@
 #include "renderer.h"
 #include "rt_shade.cuh"
 #include "bvh_build.cuh"
+#include "adaptive_squares.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -1261,6 +1262,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (!has_scene_) throw std::runtime_error("render: no scene uploaded");
     if (p.width < 2 || p.height < 2 || p.samples_per_pixel < 1 || p.max_depth < 1)
         throw std::runtime_error("render: bad image size / spp / depth");
+    if (p.adaptive == 2) throw std::runtime_error("render_device: the adaptive-squares mode produces 8-bit pixels, use render_host");
     if (p.adaptive && !count_dev) throw std::runtime_error("render: adaptive mode needs a count buffer");
     CUDA_CHECK(cudaSetDevice(device_));
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -1282,7 +1284,10 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     // partition B: the pixels of this rank's tiles
     const uint32_t* base_list = nullptr;
     size_t n_local = n_pixels;
-    if (p.tile_parts > 1) {
+    if (p.pixel_list_dev) {            // internal: an explicit list of pixels (adaptive squares)
+        base_list = p.pixel_list_dev;
+        n_local = p.n_pixel_list;
+    } else if (p.tile_parts > 1) {
         std::vector<uint32_t> mine;
         const int ts = std::max(p.tile_size, 1);
         const int tiles_x = (p.width + ts - 1) / ts;
@@ -1441,6 +1446,77 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (stats) *stats = S;
 }
 
+// engine_mode::adaptive of the reference (engine.h:151-333), level by level (adaptive_squares.cuh)
+void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_dev, float* accum_dev,
+                                       uint32_t* count_dev, RenderStats* stats)
+{
+    if (!has_scene_) throw std::runtime_error("render: no scene uploaded");
+    constexpr int kBig = 12;
+    if (p.width % kBig != 0 || p.height % kBig != 0 || p.width > 65535 || p.height > 65535)   // engine.h:182-183
+        throw std::logic_error("for adaptive strategy image size should perfectly fit big square size for now!!");
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    using namespace asq;
+    const size_t n_pixels = size_t(p.width) * size_t(p.height);
+    const uint32_t n_big = uint32_t((p.width / kBig) * (p.height / kBig));
+    std::vector<void*> bag;
+    RenderStats S;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    try {
+        int* work = dev_alloc<int>(bag, n_pixels * 3);
+        Lists L{};
+        L.squares[0] = dev_alloc<uint32_t>(bag, size_t(n_big) * 16);
+        L.squares[1] = dev_alloc<uint32_t>(bag, size_t(n_big) * 16);
+        L.pixels = dev_alloc<uint32_t>(bag, n_pixels);
+        L.counters = dev_alloc<uint32_t>(bag, 2);
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        CUDA_CHECK(cudaMemsetAsync(accum_dev, 0, n_pixels * 3 * sizeof(float), st));
+        k_sq_init<<<unsigned((n_pixels + 255) / 256), 256, 0, st>>>(work, count_dev, int(n_pixels));
+        k_sq_level0<<<(n_big + 127) / 128, 128, 0, st>>>(L, p.width, p.height, kBig);
+        uint32_t n_sq = n_big, n_px = n_big * 4;
+        int level = 0;
+        RenderParams q = p;
+        q.adaptive = 0; q.accumulate = 1; q.tile_parts = 1; q.tile_part = 0;
+        for (int size = kBig; ; size /= 2) {
+            // trace the pixels this level asked for, at full spp
+            if (n_px) {
+                q.pixel_list_dev = L.pixels; q.n_pixel_list = n_px;
+                RenderStats r;
+                render_device(cam, q, accum_dev, nullptr, &r, false);
+                S.samples += r.samples; S.rays += r.rays; S.waves += r.waves; S.launches += r.launches;
+                k_sq_commit<<<(n_px + 255) / 256, 256, 0, st>>>(L.pixels, n_px, accum_dev, p.samples_per_pixel, work, count_dev);
+            }
+            if (size < 3 || n_sq == 0) break;
+            CUDA_CHECK(cudaMemsetAsync(L.counters, 0, 2 * sizeof(uint32_t), st));
+            k_sq_decide<<<(n_sq + 127) / 128, 128, 0, st>>>(L, level, n_sq, size, work, p.width);
+            uint32_t ctr[2];
+            CUDA_CHECK(cudaMemcpyAsync(ctr, L.counters, sizeof(ctr), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            n_sq = ctr[0]; n_px = ctr[1];
+            level ^= 1;
+            S.launches += 2;
+            if (size == 3) { n_sq = 0; }        // the 3x3 squares only ask for pixels; one more pass traces them
+        }
+        k_sq_final<<<unsigned((n_pixels * 3 + 255) / 256), 256, 0, st>>>(work, int(n_pixels * 3), rgb_dev);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(cudaGetLastError());
+        float ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        S.elapsed_ms = ms;
+        S.pixels_active = S.samples / uint64_t(std::max(p.samples_per_pixel, 1));     // pixels traced
+        S.pixels_converged = n_pixels - S.pixels_active;                              // pixels interpolated
+    } catch (...) {
+        for (void* q : bag) cudaFree(q);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        throw;
+    }
+    for (void* q : bag) cudaFree(q);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) *stats = S;
+}
+
 void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
                            uint32_t* count_out, RenderStats* stats)
 {
@@ -1459,8 +1535,12 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
     }
     RenderParams q = p;
     q.accumulate = 0;
-    render_device(cam, q, I.host_accum, I.host_count, stats, false);
-    resolve_device(I.host_accum, I.host_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, I.host_rgb);
+    if (p.adaptive == 2) {
+        render_adaptive_squares(cam, q, I.host_rgb, I.host_accum, I.host_count, stats);
+    } else {
+        render_device(cam, q, I.host_accum, I.host_count, stats, false);
+        resolve_device(I.host_accum, I.host_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, I.host_rgb);
+    }
     if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, I.host_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
     if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, I.host_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
     if (count_out) CUDA_CHECK(cudaMemcpy(count_out, I.host_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));

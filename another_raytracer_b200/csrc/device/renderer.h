@@ -23,11 +23,13 @@ struct RenderParams {
     int tile_size = 32, tile_parts = 1, tile_part = 0;
     // adaptive per-pixel variance mask (0 = off): after min_spp samples a pixel stops once the standard
     // error of its luminance mean drops below rel_threshold * (mean + 0.05)
-    int adaptive = 0;
+    int adaptive = 0;                 // 1: variance mask; 2: the reference's 12/6/3 squares (render_host only)
     int adaptive_min_spp = 16;
     int adaptive_batch_spp = 8;
     double adaptive_threshold = 0.02;
     int accumulate = 0;               // 0: accum/count buffers are zeroed first
+    const uint32_t* pixel_list_dev = nullptr;   // internal: render exactly these pixels (device pointer) ...
+    uint32_t n_pixel_list = 0;                  // ... this many
 };
 
 struct RenderStats {
@@ -77,6 +79,10 @@ public:
     // Wavefront render into a device accumulation buffer (W*H*3 float sums) + per-pixel sample counts.
     void render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
                        RenderStats* stats, bool profile);
+    // engine_mode::adaptive of the reference (engine.h:151-333): corners of 12/6/3-pixel squares traced at full spp,
+    // the rest interpolated. Device buffers: rgb W*H*3, accum W*H*3 sums of the traced pixels, count = spp where traced.
+    void render_adaptive_squares(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_dev, float* accum_dev,
+                                 uint32_t* count_dev, RenderStats* stats);
     // write_color (color.h:6-22) over accum/count -> RGB8 (device buffers)
     void resolve_device(const float* accum_dev, const uint32_t* count_dev, int n_pixels, int fixed_spp, uint8_t* rgb_dev);
 

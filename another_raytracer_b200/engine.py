@@ -47,11 +47,14 @@ class SceneAlias(enum.IntEnum):
 
 class EngineMode(enum.Enum):
     """engine_mode of the reference (engine.h:10-16). On the GPU `single`, `parallel_stripes` and
-    `parallel_images` are the same fixed-spp wavefront render; `adaptive` selects the per-pixel variance mask."""
+    `parallel_images` are the same fixed-spp wavefront render; `adaptive` is the reference's own strategy (corners of
+    12/6/3-pixel squares traced, the rest interpolated: engine.h:151-333); `variance_mask` is this backend's extension
+    (north_star 3: per-pixel variance mask that re-queues only unconverged pixels)."""
     single = 0
     adaptive = 1
     parallel_stripes = 2
     parallel_images = 3
+    variance_mask = 4
 
 
 def _check(rc: int, ctx=None):
@@ -292,8 +295,8 @@ class Engine:
         if self.mode is EngineMode.adaptive and (self.width % 12 or self.height % 12):
             # engine.h:182-183 — kept so that callers relying on the reference's contract see the same failure
             raise ValueError("for adaptive strategy image size should perfectly fit big square size for now!!")
-        opt = RenderOptions(self.width, self.height, self.samples_per_pixel, self.max_depth, self.seed,
-                            mode=_abi.MODE_VARIANCE_MASK if self.mode is EngineMode.adaptive else _abi.MODE_FIXED)
+        mode = {EngineMode.adaptive: _abi.MODE_ADAPTIVE_SQUARES, EngineMode.variance_mask: _abi.MODE_VARIANCE_MASK}.get(self.mode, _abi.MODE_FIXED)
+        opt = RenderOptions(self.width, self.height, self.samples_per_pixel, self.max_depth, self.seed, mode=mode)
         rgb, stats, _, _ = self._ctx.render(self.cam, opt)
         np.copyto(np.asarray(output_image).reshape(self.height, self.width, 3), rgb)
         self.last_stats = stats

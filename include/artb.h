@@ -141,7 +141,10 @@ typedef struct artb_camera {            /* camera::camera arguments, camera.h:8-
 
 typedef enum artb_mode {
     ARTB_MODE_FIXED = 0,                /* engine_mode::single / parallel_*: spp samples for every pixel */
-    ARTB_MODE_VARIANCE_MASK = 1         /* north_star (3): per-pixel variance mask, unconverged pixels re-queued */
+    ARTB_MODE_VARIANCE_MASK = 1,        /* north_star (3): per-pixel variance mask, unconverged pixels re-queued */
+    ARTB_MODE_ADAPTIVE_SQUARES = 2      /* engine_mode::adaptive as the reference does it (engine.h:151-333): corners of
+                                           12/6/3-pixel squares at full spp, the rest interpolated; W, H multiples of 12
+                                           (else ARTB_E_ADAPTIVE_SIZE); artb_render only */
 } artb_mode;
 
 typedef struct artb_render_params {
