@@ -436,6 +436,9 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 #ifndef ARTB_PAIRS_BLOCKS
 #define ARTB_PAIRS_BLOCKS 4
 #endif
+#ifndef ARTB_PAIRS_PREFETCH
+#define ARTB_PAIRS_PREFETCH 0           // measured: prefetching ray / primitive lines during the sort costs 10 % (L1 thrash)
+#endif
 #define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory
 template <bool kBatch>
 __global__ void __launch_bounds__(ARTB_PAIRS_THREADS, ARTB_PAIRS_BLOCKS)
@@ -463,7 +466,14 @@ k_pairs(TraceIO io, SceneView s)
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             uint32_t cls = ARTB_PRIM_CLASSES;
-            if (pr[k].x != 0xffffffffu) cls = s.prim_class[pr[k].y];
+            if (pr[k].x != 0xffffffffu) {
+                cls = s.prim_class[pr[k].y];
+#if ARTB_PAIRS_PREFETCH
+                // the sort below takes three barriers: time for the ray record (DRAM -> L2) and the primitive (-> L1)
+                if (!kBatch) prefetch_l2(io.rays.at(pr[k].x));
+                prefetch_l1(s.prims + pr[k].y);
+#endif
+            }
             cls_rank[k] = (cls << 24) | atomicAdd(&class_count[cls], 1u);
         }
         __syncthreads();

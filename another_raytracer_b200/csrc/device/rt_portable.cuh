@@ -174,6 +174,15 @@ ARTB_HD void prefetch_l1(const void* p)
 #endif
 }
 
+ARTB_HD void prefetch_l2(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 } // namespace artb
 
 #endif

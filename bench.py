@@ -226,6 +226,8 @@ def run_cuda_arm(args, wl):
     ctx.upload(scene)
     bvh_build = ctx.last_bvh_build
     cam = scene.camera(W, H)
+    tiles = args.partition == "tiles"
+    step_count = torch.zeros((H, W), dtype=torch.int32, device=dev) if args.variance_mask else None
     step_accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     total_accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
     rgb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
@@ -240,8 +242,13 @@ def run_cuda_arm(args, wl):
     def one_step(k: int) -> dict:
         flush.zero_()                                                    # L2 flush between timed iterations
         torch.cuda.synchronize()
-        opt = A.RenderOptions(W, H, S, seed=args.seed, stream=rank, sample_begin=(k * world + rank) * S, profile=True)
-        st = ctx.render_device(cam, opt, step_accum.data_ptr())         # blocking; accum cleared by the call
+        # partition A (default): every rank renders S samples of every pixel on its own Philox stream and index range;
+        # partition B (--partition tiles, BASELINE configs[4]): every rank renders S samples of its interleaved tiles
+        opt = A.RenderOptions(W, H, S, seed=args.seed, stream=0 if tiles else rank,
+                              sample_begin=(k if tiles else k * world + rank) * S, profile=True,
+                              tile_parts=world if tiles else 1, tile_part=rank if tiles else 0,
+                              mode=1 if args.variance_mask else 0)
+        st = ctx.render_device(cam, opt, step_accum.data_ptr(), step_count.data_ptr() if step_count is not None else None)
         D.reduce_frames(step_accum)                                      # the one exchange of the path
         if rank == 0:
             total_accum.add_(step_accum)
@@ -273,7 +280,7 @@ def run_cuda_arm(args, wl):
     # resolve the accumulated image on rank 0 (write_color) and keep a checksum so the work cannot be skipped
     checksum = None
     if rank == 0:
-        ctx.resolve_device(total_accum.data_ptr(), None, W * H, S * world * args.steps, rgb.data_ptr())
+        ctx.resolve_device(total_accum.data_ptr(), None, W * H, S * (1 if tiles else world) * args.steps, rgb.data_ptr())
         torch.cuda.synchronize()
         checksum = int(rgb.to(torch.int64).sum().item())
 
@@ -335,7 +342,7 @@ def run_cuda_arm(args, wl):
             "warmup": args.warmup, "ms_per_step": dev_ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "scene_alias": alias, "width": W, "height": H, "max_depth": 50,
-                       "spp_per_step": S, "full_config_spp": wl["full_spp"], "partition": f"samples x{world}", "pool_paths": args.pool,
+                       "spp_per_step": S, "full_config_spp": wl["full_spp"], "partition": f"{args.partition} x{world}", "variance_mask": bool(args.variance_mask), "pool_paths": args.pool,
                        "seed": args.seed, "l2": "256 MiB flush buffer written between timed steps; path pool > L2",
                        "device_bvh_build_ms": bvh_build["build_ms"] if bvh_build["n_nodes"] else None},
             "mrays_per_sec": rays / (dev_ms_max * 1e-3) / 1e6, "rays_per_sample": rays / max(samples, 1),
@@ -362,6 +369,8 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
+    ap.add_argument("--variance-mask", action="store_true", help="per-pixel variance mask (adaptive subsampling, north_star 3)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
