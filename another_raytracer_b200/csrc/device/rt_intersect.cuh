@@ -298,7 +298,7 @@ ARTB_HD BoxRay make_box_ray(const TravRay& t)
     uint32_t oct = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        float id = 1.0f / t.d[a];
+        float id = rcp_rn(t.d[a]);
         id = fminf(fmaxf(id, -1e20f), 1e20f);
         if (!(id == id)) id = 1e20f;
         b.inv[a] = id;
