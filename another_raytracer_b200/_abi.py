@@ -59,7 +59,8 @@ class FlatSceneView(C.Structure):
                 ("images", C.c_void_p), ("n_images", C.c_uint32),
                 ("texels", C.c_void_p), ("n_texel_bytes", C.c_uint64),
                 ("perlins", C.c_void_p), ("n_perlins", C.c_uint32),
-                ("n_media", C.c_uint32), ("background", C.c_double * 3)]
+                ("n_media", C.c_uint32), ("background", C.c_double * 3),
+                ("ref_nodes", C.c_void_p), ("n_ref_nodes", C.c_uint32)]
 
 
 class Hit(C.Structure):

@@ -228,6 +228,7 @@ int artb_scene_get_flat(const artb_scene* s, artb_flat_scene* out)
     out->perlins = f.perlins.data(); out->n_perlins = uint32_t(f.perlins.size());
     out->n_media = f.n_media;
     for (int k = 0; k < 3; ++k) out->background[k] = f.background[k];
+    out->ref_nodes = f.ref_nodes.data(); out->n_ref_nodes = uint32_t(f.ref_nodes.size());
     return ARTB_OK;
 }
 
@@ -264,6 +265,7 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
         copy(fs.images, f->images, f->n_images);
         copy(fs.texels, f->texels, f->n_texel_bytes);
         copy(fs.perlins, f->perlins, f->n_perlins);
+        copy(fs.ref_nodes, f->ref_nodes, f->n_ref_nodes);
         fs.n_world_prims = f->n_world_prims; fs.n_media = f->n_media;
         fs.n_global_prims = f->n_global_prims; fs.bvh_depth = f->bvh_depth;
         // every constant_medium must sit at the END of the global range (the device tests media after the traversal)
@@ -281,6 +283,15 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
             if (p.type == PRIM_MEDIUM && (p.g[1] < fs.n_world_prims || p.g[1] + p.g[2] > double(fs.prims.size())))
                 throw std::logic_error("flat scene: medium boundary range out of bounds");
         }
+        for (size_t i = 0; i < fs.ref_nodes.size(); ++i) {
+            const FlatRefNode& rn = fs.ref_nodes[i];
+            if (rn.parent < -1 || rn.parent >= int32_t(i) || rn.xform >= fs.xforms.size() ||
+                rn.depth != (rn.parent < 0 ? 0 : fs.ref_nodes[size_t(rn.parent)].depth + 1))
+                throw std::logic_error("flat scene: bad reference bvh node");
+        }
+        for (uint32_t i = 0; i < fs.n_world_prims; ++i)
+            if (fs.prims[i].type != PRIM_MEDIUM && !(fs.prims[i].g[9] >= 0 && fs.prims[i].g[9] <= double(fs.ref_nodes.size())))
+                throw std::logic_error("flat scene: primitive refers to a missing reference bvh node (g[9])");
         // BVH primitives without nodes: allowed — Renderer::upload then builds the tree on the device (bvh_build.cuh)
         if (fs.bvh_depth < 0 || fs.bvh_depth > 24) throw std::logic_error("flat scene: bvh_depth out of range");
         for (const FlatNode8& n : fs.nodes) {

@@ -38,7 +38,8 @@ enum : uint32_t {
 };
 
 struct ARTB_ALIGN(16) FlatPrim {      // 96 B
-    double g[10];
+    double g[10];         // every type but PRIM_MEDIUM: g[9] = 1 + index of the innermost reference bvh_node that encloses
+                          // the primitive (FlatRefNode, below), 0 = none
     uint32_t type;
     uint32_t material;
     uint32_t xform;       // 0 = identity
@@ -69,6 +70,18 @@ struct ARTB_ALIGN(16) FlatNode8 {     // 80 B
     uint8_t qhi[3][8];
 };
 #define ARTB_MAX_LEAF_PRIMS 3
+
+// One bvh_node of the REFERENCE's own trees (bvh.h:22-25), kept only to break exact ties the way the reference does:
+// bvh_node::hit tests its box with the current closest t as t_max, and aabb::hit rejects t_max <= t_min (aabb.h:25,
+// strict), so a later leaf whose enclosing boxes are entered exactly AT the closest t so far is never visited and
+// cannot overwrite an equal-t hit (rt_intersect.cuh: tie_later_wins). Coincident faces of adjacent boxes do this.
+struct ARTB_ALIGN(16) FlatRefNode {   // 64 B
+    double lo[3], hi[3];  // bvh_node::box, in the space of its transform chain
+    int32_t parent;       // enclosing reference bvh_node (through lists and wrappers), -1 = none
+    uint32_t xform;       // transform chain in force at the node
+    int32_t depth;        // number of enclosing reference bvh_nodes
+    uint32_t pad;
+};
 
 enum : uint32_t { XFORM_TRANSLATE = 0, XFORM_ROTATE_Y = 1 };
 
@@ -123,6 +136,7 @@ inline uint32_t prim_class_of(uint32_t type, uint32_t xform)
 
 struct SceneView {
     const FlatPrim* prims;
+    const FlatRefNode* ref_nodes;     // reference bvh_nodes for exact tie-breaking, or nullptr (ties then go to the larger dfs_id)
     const uint8_t* prim_class;        // per primitive: prim_class_of(type, xform) (device only; built by Renderer::upload)
     const uint8_t* prim_mat_type;     // per primitive: type of its material = the shade queue a hit goes to (device only)
     const FlatNode8* nodes;

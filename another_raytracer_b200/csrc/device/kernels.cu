@@ -29,7 +29,7 @@ namespace artb {
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
     throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
-// Path state: ONE 128-byte line per pool slot — ray (64 B) | aux (32 B) | hit (16 B) | pad — so that a kernel that
+// Path state: ONE 128-byte line per pool slot — ray (64 B) | aux (32 B) | hit (16 B) | ties (16 B) — so that a kernel that
 // needs the ray, the path's bookkeeping and its hit record touches exactly one aligned line (four sectors) per path.
 // (As three separate arrays the 16- and 32-byte records dragged their neighbours' sectors along on every random
 // access: ncu showed 320 B of DRAM reads per ray in k_finish for 116 B of payload.)
@@ -42,6 +42,7 @@ struct Strided {
 struct __align__(16) PathRay { double o[3], d[3], tm, pad; };                       // 64 B
 struct __align__(16) PathAux { float thr[3]; uint32_t pixel, sample, rng_block, depth, pad; };   // 32 B
 struct __align__(16) PathHit { double t; int32_t prim; uint32_t dfs; };             // 16 B: the best hit so far
+struct __align__(16) PathTie { uint32_t n; uint32_t prim[3]; };                     // 16 B: other candidates with the SAME t (merge_hit)
 
 // Queues written by k_extend (one per material type + the free-slot list) and their counters. Counters are
 // double-buffered by wave parity so that each kernel can reset, from one thread, the counters that NEITHER it nor
@@ -71,6 +72,7 @@ struct WaveBuffers {
     Strided<PathRay> rays;            // views into the pool of 128-byte path records
     Strided<PathAux> aux;
     Strided<PathHit> hits;
+    Strided<PathTie> ties;
     uint32_t* q_extend[2];
     uint32_t* q_regen[2];
     uint32_t* q_shade;                // MAT_COUNT queues of `pool` entries, back to back
@@ -247,6 +249,7 @@ struct PairBuf {
 struct TraceIO {
     const uint32_t* n_ptr;            // number of rays of this launch (device memory)
     const uint32_t* list;             // ray ids (path slots); nullptr: 0..n-1
+    Strided<PathTie> ties;            // one record per ray id: candidates whose t equals the record's (exact ties)
     Strided<PathHit> hits;            // one record per ray id: the best hit so far; prim == ARTB_HIT_OVERFLOW: some of the
                                       // ray's pairs did not fit, the overflow pass traces it
     PairBuf pb;
@@ -298,21 +301,53 @@ __device__ __forceinline__ void peek_hit(const PathHit* h, unsigned long long& l
     asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(h) : "memory");
 }
 
-__device__ __forceinline__ void merge_hit(PathHit* h, unsigned long long cur_lo, unsigned long long cur_hi, double t, uint32_t prim,
-                                          uint32_t dfs)
+__device__ __forceinline__ bool cas_hit(PathHit* h, unsigned long long& cur_lo, unsigned long long& cur_hi, unsigned long long new_lo,
+                                        unsigned long long new_hi)
 {
-    const unsigned long long new_lo = (unsigned long long)__double_as_longlong(t);
-    const unsigned long long new_hi = (unsigned long long)prim | ((unsigned long long)dfs << 32);
+    unsigned long long old_lo, old_hi;
+    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(old_lo), "=l"(old_hi) : "l"(cur_lo), "l"(cur_hi), "l"(new_lo), "l"(new_hi), "l"(h) : "memory");
+    const bool done = old_lo == cur_lo && old_hi == cur_hi;
+    cur_lo = old_lo; cur_hi = old_hi;
+    return done;
+}
+
+// Merge a candidate into a ray's record (k_pairs). An exact tie (the candidate's t EQUALS the record's) is not decided
+// here: the reference's rule for it needs the boxes of its own bvh_nodes and the world-space ray (rt_intersect.cuh:
+// hit_replaces), which would cost this kernel a call and a stack frame for something that happens a few times per
+// million rays. The record keeps the later leaf and gets ARTB_HIT_TIED set, the other leaf goes to the ray's tie list;
+// k_finish — which has the ray — replays the tied leaves in the reference's order.
+#define ARTB_HIT_TIED 0x80000000u     // bit 31 of PathHit::dfs
+template <bool kBatch>
+__device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, unsigned long long cur_lo, unsigned long long cur_hi,
+                                          double t, uint32_t prim, uint32_t dfs)
+{
+    PathHit* h = io.hits.at(ray_id);
     for (;;) {
+        unsigned long long new_lo = (unsigned long long)__double_as_longlong(t);
+        unsigned long long new_hi = (unsigned long long)prim | ((unsigned long long)dfs << 32);
         const double cur_t = __longlong_as_double((long long)cur_lo);
-        if (int32_t(uint32_t(cur_hi)) == ARTB_HIT_OVERFLOW) return;
-        if (!hit_is_better(t, dfs, cur_t, int32_t(uint32_t(cur_hi)), uint32_t(cur_hi >> 32))) return;
-        unsigned long long old_lo, old_hi;
-        asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
-                     "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
-                     : "=l"(old_lo), "=l"(old_hi) : "l"(cur_lo), "l"(cur_hi), "l"(new_lo), "l"(new_hi), "l"(h) : "memory");
-        if (old_lo == cur_lo && old_hi == cur_hi) return;
-        cur_lo = old_lo; cur_hi = old_hi;
+        const int32_t cur_prim = int32_t(uint32_t(cur_hi));
+        if (cur_prim == ARTB_HIT_OVERFLOW) return;
+        uint32_t other = 0xffffffffu;                             // the leaf that does NOT stay in the record on a tie
+        if (cur_prim >= 0) {
+            if (t > cur_t) return;
+            if (t == cur_t) {
+                const uint32_t cur_dfs = uint32_t(cur_hi >> 32);
+                if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
+                else other = uint32_t(cur_prim);
+                new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
+            }
+        } else if (!(t <= cur_t)) return;
+        if (cas_hit(h, cur_lo, cur_hi, new_lo, new_hi)) {
+            if (other != 0xffffffffu) {
+                PathTie* tie = io.ties.at(ray_id);
+                const uint32_t k = atomicAdd(&tie->n, 1u);
+                if (k < 3u) tie->prim[k] = other;
+            }
+            return;
+        }
     }
 }
 
@@ -392,6 +427,7 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
                     br = make_box_ray(make_trav_ray(r));
                     collect_begin(col, has_tree);
                     store_hit(io.hits.at(id), io.t_max, -1, 0u);
+                    io.ties.at(id)->n = 0u;
                     active = true;
                     spilled = false;
                 }
@@ -523,11 +559,27 @@ k_pairs(TraceIO io, SceneView s)
                 ok = surface_t(p, q, io.t_min, io.t_max, t);
             }
             warp_sync();
-            if (ok && t == t) merge_hit(io.hits.at(pq.x), cur_lo, cur_hi, t, pq.y, dfs);
+            if (ok && t == t) merge_hit<kBatch>(io, pq.x, cur_lo, cur_hi, t, pq.y, dfs);
             warp_sync();
         }
         __syncthreads();
     }
+}
+
+// Several leaves report the same t: test them again one by one in the reference's depth-first order, as
+// hittable_list::hit / bvh_node::hit would (test_surface applies the exact rule, hit_replaces). Rare: out of line.
+__device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie, uint32_t n_tied, uint32_t record_prim, const DRay& r,
+                                         double t_min, double t_max, ClosestHit& best)
+{
+    uint32_t cand[4];
+    for (uint32_t k = 0; k < n_tied; ++k) cand[k] = tie->prim[k];
+    cand[n_tied] = record_prim;
+    for (uint32_t a = 1; a <= n_tied; ++a)
+        for (uint32_t b = a; b > 0 && s.prims[cand[b - 1]].dfs_id > s.prims[cand[b]].dfs_id; --b) {
+            const uint32_t tmp = cand[b]; cand[b] = cand[b - 1]; cand[b - 1] = tmp;
+        }
+    best.t = t_max; best.prim = -1; best.dfs = 0;
+    for (uint32_t k = 0; k <= n_tied; ++k) test_surface(s, cand[k], r, t_min, best);
 }
 
 #ifndef ARTB_FINISH_DEFER
@@ -577,13 +629,18 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
             if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
             else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
         }
-        const bool overflow = ph.prim == ARTB_HIT_OVERFLOW;
+        // flagged by k_traverse (pairs did not fit), or more leaves tied than the list holds: the one-phase pass traces the ray
+        const bool tied = valid && ph.prim >= 0 && (ph.dfs & ARTB_HIT_TIED) != 0u;
+        uint32_t n_tied = 0;
+        if (tied) n_tied = io.ties.at(id)->n;
+        const bool overflow = ph.prim == ARTB_HIT_OVERFLOW || n_tied > 3u;
         queue_push(io.q_overflow, io.n_overflow, overflow, id, lane);
         const bool live = valid && !overflow;
         int key = -1;
         if (live) {
             ClosestHit best;
-            best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs;
+            best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs & ~ARTB_HIT_TIED;
+            if (tied) replay_ties(s, io.ties.at(id), n_tied, uint32_t(ph.prim), r, io.t_min, io.t_max, best);
             for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
             if (s.n_global_media) {
                 MediumXi xi;
@@ -1000,6 +1057,7 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     w.rays = { recs, ARTB_PATH_STRIDE };
     w.aux = { recs + sizeof(PathRay), ARTB_PATH_STRIDE };
     w.hits = { recs + sizeof(PathRay) + sizeof(PathAux), ARTB_PATH_STRIDE };
+    w.ties = { recs + sizeof(PathRay) + sizeof(PathAux) + sizeof(PathHit), ARTB_PATH_STRIDE };
     for (int k = 0; k < 2; ++k) {
         w.q_extend[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
         w.q_regen[k] = dev_alloc<uint32_t>(impl_->pool_allocs, pool_paths);
@@ -1046,6 +1104,7 @@ void Renderer::upload(const FlatScene& fs)
     uint64_t bytes = 0;
     SceneView v{};
     v.prims = dev_upload(impl_->scene_allocs, fs.prims, st, bytes);
+    v.ref_nodes = fs.ref_nodes.empty() ? nullptr : dev_upload(impl_->scene_allocs, fs.ref_nodes, st, bytes);
     std::vector<uint8_t> prim_class(fs.prims.size());
     for (size_t i = 0; i < fs.prims.size(); ++i) prim_class[i] = uint8_t(prim_class_of(fs.prims[i].type, fs.prims[i].xform));
     v.prim_class = dev_upload(impl_->scene_allocs, prim_class, st, bytes);
@@ -1098,6 +1157,7 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
         size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
         if (const char* e = getenv("ARTB_PAIR_CAPACITY")) pair_capacity = std::max<size_t>(size_t(atoll(e)), 1);
         PathHit* hits = dev_alloc<PathHit>(bag, cap);
+        PathTie* ties = dev_alloc<PathTie>(bag, cap);
         uint2* pairs = dev_alloc<uint2>(bag, pair_capacity);
         uint32_t* region_count = dev_alloc<uint32_t>(bag, ARTB_MAX_REGIONS);
         uint32_t* overflow = dev_alloc<uint32_t>(bag, cap);
@@ -1111,6 +1171,7 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
             CUDA_CHECK(cudaStreamSynchronize(st));               // `init` lives on this stack frame
             TraceIO io{};
             io.n_ptr = ctr; io.list = nullptr; io.hits = { reinterpret_cast<char*>(hits), uint32_t(sizeof(PathHit)) };
+            io.ties = { reinterpret_cast<char*>(ties), uint32_t(sizeof(PathTie)) };
             impl_->set_pair_buffer(view_, io, pairs, pair_capacity, region_count);
             io.cursor_traverse = ctr + 1; io.q_overflow = overflow; io.n_overflow = ctr + 3;
             io.t_min = t_min; io.t_max = t_max;
@@ -1399,7 +1460,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                 }
                 if (two_phase) {
                     TraceIO io{};
-                    io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits;
+                    io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits; io.ties = w.ties;
                     I.set_pair_buffer(view_, io, w.pairs, w.pair_capacity, w.region_count);
                     io.cursor_traverse = &w.c->cursor[0];
                     io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;

@@ -234,6 +234,60 @@ ARTB_HD bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, 
     return true;
 }
 
+// ---- exact ties ---------------------------------------------------------------------------------------------------
+// aabb::hit as the reference evaluates it (aabb.h:16-29): 1/d in double, strict rejection when the interval collapses
+ARTB_HD bool ref_aabb_hit(const FlatRefNode& n, const DRay& r, double t_min, double t_max)
+{
+    const double o[3] = { r.o.x, r.o.y, r.o.z }, d[3] = { r.d.x, r.d.y, r.d.z };
+    for (int a = 0; a < 3; ++a) {
+        const double invD = 1.0 / d[a];
+        double t0 = (n.lo[a] - o[a]) * invD;
+        double t1 = (n.hi[a] - o[a]) * invD;
+        if (invD < 0.0) { const double tmp = t0; t0 = t1; t1 = tmp; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    return true;
+}
+
+ARTB_HD int prim_ref_node(const FlatPrim& p) { return p.type == PRIM_MEDIUM ? -1 : int(p.g[9]) - 1; }
+
+// Two leaves report the SAME t. In the reference the one tested later overwrites the earlier one (every leaf accepts
+// t == t_max) — if it is tested at all: by then t_max is that very t, and every bvh_node between the two leaves' common
+// ancestor and the later leaf first asks its box with it (bvh.cpp:45, aabb.h:25: t_max <= t_min rejects). Replays those
+// box tests with the reference's arithmetic. Rare (coincident faces of adjacent boxes), hence not inlined.
+ARTB_HD_NOINLINE bool tie_later_wins(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim_earlier,
+                                     uint32_t prim_later)
+{
+    if (!s.ref_nodes) return true;
+    int a = prim_ref_node(s.prims[prim_earlier]), b = prim_ref_node(s.prims[prim_later]);
+    // lowest common ancestor of the two chains of reference nodes (-1: none, the leaves meet in a plain list)
+    int x = a, y = b;
+    while (x != y) {
+        const int dx = x < 0 ? -1 : s.ref_nodes[x].depth, dy = y < 0 ? -1 : s.ref_nodes[y].depth;
+        if (dx >= dy) x = s.ref_nodes[x].parent;
+        else y = s.ref_nodes[y].parent;
+    }
+    for (int n = b; n != x; n = s.ref_nodes[n].parent) {
+        const FlatRefNode& node = s.ref_nodes[n];
+        if (!ref_aabb_hit(node, to_object_space(s, node.xform, world), t_min, t)) return false;
+    }
+    return true;
+}
+
+// The merge rule, i.e. what hittable_list::hit / bvh_node::hit do by narrowing t_max (hittable_list.cpp:11-15,
+// bvh.cpp:48-49): a candidate replaces the best iff it is closer; at equal t the leaf that comes later in the
+// reference's depth-first order wins, provided the reference would have visited it (tie_later_wins).
+ARTB_HD bool hit_replaces(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim, uint32_t dfs, double best_t,
+                          int32_t best_prim, uint32_t best_dfs)
+{
+    if (t < best_t || best_prim < 0) return t <= best_t;
+    if (t != best_t) return false;
+    if (dfs > best_dfs) return tie_later_wins(s, world, t_min, t, uint32_t(best_prim), prim);
+    return !tie_later_wins(s, world, t_min, t, prim, uint32_t(best_prim));
+}
+
 // ---- closest hit ----------------------------------------------------------------------------------
 struct ClosestHit { double t; int32_t prim; uint32_t dfs; };
 
@@ -245,7 +299,7 @@ ARTB_HD void test_surface(const SceneView& s, uint32_t i, const DRay& world, dou
     bool ok;
     if (p.xform) ok = surface_t(p, to_object_space(s, p.xform, world), t_min, best.t, t);
     else ok = surface_t(p, world, t_min, best.t, t);
-    if (ok && (t < best.t || best.prim < 0 || p.dfs_id > best.dfs)) {
+    if (ok && hit_replaces(s, world, t_min, t, i, p.dfs_id, best.t, best.prim, best.dfs)) {
         best.t = t; best.prim = int32_t(i); best.dfs = p.dfs_id;
     }
 }
@@ -576,14 +630,6 @@ ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float 
     return true;
 }
 
-// The merge rule of phase 2, i.e. what hittable_list::hit / bvh_node::hit do by narrowing t_max (hittable_list.cpp:11-15,
-// bvh.cpp:48-49): a candidate replaces the best iff it is closer, or equally close and later in the reference's
-// depth-first order.
-ARTB_HD bool hit_is_better(double t, uint32_t dfs, double best_t, int32_t best_prim, uint32_t best_dfs)
-{
-    return t < best_t || (t == best_t && (best_prim < 0 || dfs > best_dfs));
-}
-
 // one ray per lane from start to end (k_trace_batch, hostsim); k_extend drives the same pieces itself so that it
 // can hand a fresh ray to a lane as soon as its old one is finished
 template <class NodePtr>
@@ -631,7 +677,7 @@ ARTB_HD ClosestHit closest_hit_two_phase(const SceneView& s, NodePtr nodes, cons
         if (p.type == PRIM_MEDIUM) continue;
         double t;
         const bool ok = p.xform ? surface_t(p, to_object_space(s, p.xform, ray), t_min, t_max, t) : surface_t(p, ray, t_min, t_max, t);
-        if (ok && hit_is_better(t, p.dfs_id, best.t, best.prim, best.dfs)) { best.t = t; best.prim = int32_t(ids[k]); best.dfs = p.dfs_id; }
+        if (ok && hit_replaces(s, ray, t_min, t, ids[k], p.dfs_id, best.t, best.prim, best.dfs)) { best.t = t; best.prim = int32_t(ids[k]); best.dfs = p.dfs_id; }
     }
     const uint32_t n_surf = s.n_global_prims - s.n_global_media;
     for (uint32_t i = 0; i < n_surf; ++i) {

@@ -52,6 +52,7 @@ private:
     FlatScene out;
     std::vector<Item> world_items, boundary_items;
     uint32_t next_id = 0;
+    int cur_ref = -1;                       // innermost reference bvh_node being walked
     std::vector<FlatXformOp> chain;
     int chain_id = 0;                       // -1: current chain not materialised yet
     std::unordered_map<const void*, uint32_t> mat_ids, tex_ids, img_ids, perlin_ids;
@@ -214,6 +215,7 @@ private:
         it.prim.material = material_id(m);
         it.prim.xform = current_xform();
         it.prim.dfs_id = id;
+        it.prim.g[9] = double(cur_ref + 1);      // innermost enclosing reference bvh_node (no primitive type uses g[9])
         it.box = to_world(object_box);
         dst.push_back(it);
     }
@@ -232,8 +234,18 @@ private:
                 const auto& n = static_cast<const bvh_node&>(h);
                 bool flat = false;
                 for (int k = 0; k < 3; ++k) flat = flat || !(n.box.min()[k] < n.box.max()[k]);
+                // remember the reference's own node: its box decides exact ties (FlatRefNode)
+                FlatRefNode rn{};
+                for (int k = 0; k < 3; ++k) { rn.lo[k] = n.box.min()[k]; rn.hi[k] = n.box.max()[k]; }
+                rn.parent = cur_ref;
+                rn.xform = current_xform();
+                rn.depth = cur_ref < 0 ? 0 : out.ref_nodes[size_t(cur_ref)].depth + 1;
+                const int saved_ref = cur_ref;
+                cur_ref = int(out.ref_nodes.size());
+                out.ref_nodes.push_back(rn);
                 walk(*n.left, culled || flat, dst);
                 if (n.left.get() != n.right.get()) walk(*n.right, culled || flat, dst);
+                cur_ref = saved_ref;
                 break;
             }
             case hittable_kind::translate: {

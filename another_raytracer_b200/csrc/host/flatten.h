@@ -35,6 +35,7 @@ struct FlatScene {
     std::vector<FlatImage> images;
     std::vector<unsigned char> texels;
     std::vector<FlatPerlin> perlins;
+    std::vector<FlatRefNode> ref_nodes;   // the reference's bvh_nodes (tie-breaking only)
     uint32_t n_world_prims = 0;
     uint32_t n_global_prims = 0;
     uint32_t n_global_media = 0;          // the last n_global_media globals are the scene's constant_media

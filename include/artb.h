@@ -91,6 +91,9 @@ typedef struct artb_flat_scene {
     const void* perlins;    uint32_t n_perlins;                /* FlatPerlin[], 9216 B     */
     uint32_t n_media;
     double background[3];
+    const void* ref_nodes;  uint32_t n_ref_nodes;              /* FlatRefNode[], 64 B: the reference's own bvh_nodes, used only
+                                                                  to break exact-t ties as bvh_node::hit does (may be NULL/0:
+                                                                  ties then go to the larger dfs_id); FlatPrim::g[9] = 1 + index */
 } artb_flat_scene;
 
 /* view of the arrays owned by `s` (valid until artb_scene_free) */

@@ -33,6 +33,7 @@ int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, doub
     s.images = static_cast<const FlatImage*>(f->images);
     s.texels = f->texels;
     s.perlins = static_cast<const FlatPerlin*>(f->perlins);
+    s.ref_nodes = f->n_ref_nodes ? static_cast<const FlatRefNode*>(f->ref_nodes) : nullptr;
     s.n_prims = f->n_prims; s.n_world_prims = f->n_world_prims; s.n_global_prims = f->n_global_prims;
     s.n_nodes = f->n_nodes; s.n_media = f->n_media; s.n_xforms = f->n_xforms;
     s.n_materials = f->n_materials; s.n_textures = f->n_textures;
