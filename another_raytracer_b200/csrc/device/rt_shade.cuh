@@ -50,16 +50,16 @@ __device__ inline HitInfo make_hit_info(const SceneView& s, int32_t prim, const 
     h.t = t; h.u = 0; h.v = 0;          // moving_sphere / constant_medium leave u,v untouched (Q8); they are unused there
     h.material = p.material;
 
-    // rays at every level of the transform chain: level 0 = world, level n = object space
-    DRay level[9];
-    level[0] = world;
+    // the ray in object space, and its DIRECTION at every level of the transform chain (the wrappers re-orient the
+    // normal against their own inner ray on the way out). Untransformed primitives — most hits — touch no local memory.
+    DRay r = world;
+    d3 inner_dir[8];
     uint32_t n_ops = 0, first_op = 0;
     if (p.xform) {
         const FlatXform xf = s.xforms[p.xform];
         n_ops = xf.n_ops; first_op = xf.first_op;
-        for (uint32_t i = 0; i < n_ops; ++i) { level[i + 1] = level[i]; xform_op_in(s.xform_ops[first_op + i], level[i + 1]); }
+        for (uint32_t i = 0; i < n_ops; ++i) { xform_op_in(s.xform_ops[first_op + i], r); inner_dir[i] = r.d; }
     }
-    const DRay& r = level[n_ops];
 
     h.p = ray_at(r, t);
     switch (p.type) {
@@ -110,14 +110,14 @@ __device__ inline HitInfo make_hit_info(const SceneView& s, int32_t prim, const 
         const FlatXformOp& op = s.xform_ops[first_op + i];
         if (op.type == XFORM_TRANSLATE) {
             h.p = h.p + mk3(op.a, op.b, op.c);
-            set_face_normal(h, level[i + 1].d, h.normal);
+            set_face_normal(h, inner_dir[i], h.normal);
         } else {
             const double px = op.b * h.p.x + op.a * h.p.z;
             const double pz = -op.a * h.p.x + op.b * h.p.z;
             const double nx = op.b * h.normal.x + op.a * h.normal.z;
             const double nz = -op.a * h.normal.x + op.b * h.normal.z;
             h.p.x = px; h.p.z = pz;
-            set_face_normal(h, level[i + 1].d, mk3(nx, h.normal.y, nz));
+            set_face_normal(h, inner_dir[i], mk3(nx, h.normal.y, nz));
         }
     }
     return h;
