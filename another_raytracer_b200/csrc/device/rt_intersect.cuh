@@ -397,7 +397,7 @@ ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t
 template <int J>
 ARTB_HD void node8_child(uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4, uint32_t fy4, uint32_t fz4, const float* A,
                          const float* Bn, const float* Bf, float t_min, float t_best, uint32_t child_bits4, uint32_t bit_index4,
-                         uint32_t one, uint32_t& hitmask)
+                         uint32_t one, uint32_t& hitmask, float& tn_min)
 {
     constexpr uint32_t kSel = 0x7604u | (uint32_t(J) << 4);
     const float tnx = fmaf(as_float(byte_perm_sel<kSel>(nx4, one)), A[0], Bn[0]);
@@ -412,11 +412,14 @@ ARTB_HD void node8_child(uint32_t nx4, uint32_t ny4, uint32_t nz4, uint32_t fx4,
         const uint32_t bits = (child_bits4 >> (8 * J)) & 0xffu;
         const uint32_t index = (bit_index4 >> (8 * J)) & 0xffu;
         hitmask |= bits << index;
+        tn_min = fminf(tn_min, tn);
     }
 }
 
+// tn_min (in/out): lowered to the smallest near-plane parameter among the children that were hit — a conservative lower
+// bound (the pads only widen the interval) of the t of anything the ray can hit inside them.
 ARTB_HD uint32_t node8_hits(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3, const uint4 n4, const BoxRay& r,
-                            float t_min, float t_best, uint32_t one /* SceneView::one_bits */)
+                            float t_min, float t_best, uint32_t one /* SceneView::one_bits */, float& tn_min)
 {
     float A[3], Bn[3], Bf[3];
     const float p[3] = { as_float(n0.x), as_float(n0.y), as_float(n0.z) };
@@ -444,10 +447,10 @@ ARTB_HD uint32_t node8_hits(const uint4 n0, const uint4 n1, const uint4 n2, cons
         const uint32_t nx4 = px ? qlox : qhix, fx4 = px ? qhix : qlox;
         const uint32_t ny4 = py ? qloy : qhiy, fy4 = py ? qhiy : qloy;
         const uint32_t nz4 = pz ? qloz : qhiz, fz4 = pz ? qhiz : qloz;
-        node8_child<0>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
-        node8_child<1>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
-        node8_child<2>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
-        node8_child<3>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask);
+        node8_child<0>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask, tn_min);
+        node8_child<1>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask, tn_min);
+        node8_child<2>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask, tn_min);
+        node8_child<3>(nx4, ny4, nz4, fx4, fy4, fz4, A, Bn, Bf, t_min, t_best, child_bits4, bit_index4, one, hitmask, tn_min);
     }
     return hitmask;
 }
@@ -526,7 +529,8 @@ ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Trav
         const uint4* q = reinterpret_cast<const uint4*>(nodes + (tv.ng.x + rel));
         const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
         ARTB_STAT(stats, nodes);
-        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f, s.one_bits);
+        float tn_unused = 0.f;
+        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f, s.one_bits, tn_unused);
         tv.ng.x = n1.x;
         tv.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
         tv.pg.x = n1.y;
@@ -602,8 +606,9 @@ ARTB_HD bool collect_pop(Collector& c, const uint2* stack)
 
 template <class NodePtr>
 ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
-                          uint32_t& prim_base, uint32_t& prim_mask, uint32_t one_bits, TraversalStats* stats)
+                          uint32_t& prim_base, uint32_t& prim_mask, float& tn_min, uint32_t one_bits, TraversalStats* stats)
 {
+    tn_min = INFINITY;
     const uint32_t hits = c.ng.y;
     const int bit = find_msb(hits);
     c.ng.y &= ~(1u << bit);
@@ -613,7 +618,7 @@ ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float 
     const uint4* q = reinterpret_cast<const uint4*>(nodes + (c.ng.x + rel));
     const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
     ARTB_STAT(stats, nodes);
-    const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f, one_bits);
+    const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, t_max_f, one_bits, tn_min);
     c.ng.x = n1.x;
     c.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
     prim_base = n1.y;
@@ -626,7 +631,8 @@ ARTB_HD bool collect_step(NodePtr nodes, const BoxRay& br, float t_min_f, float 
 {
     prim_mask = 0u;
     if (!collect_pop(c, stack)) return false;
-    collect_node(nodes, br, t_min_f, t_max_f, c, stack, prim_base, prim_mask, one_bits, stats);
+    float tn_min;
+    collect_node(nodes, br, t_min_f, t_max_f, c, stack, prim_base, prim_mask, tn_min, one_bits, stats);
     return true;
 }
 
