@@ -482,10 +482,12 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
             uint32_t pos = wbase + incl - cnt;
 #endif
             if (pos + cnt <= cap) {
+                const uint32_t tn_bits = pack_pair(0u, 0u, tn_min).y;       // the same bound for every pair of this step
                 while (prim_mask) {
                     const int b = find_msb(prim_mask);
                     prim_mask &= ~(1u << b);
-                    region[pos++] = pack_pair(id, prim_base + uint32_t(b), tn_min);
+                    const uint32_t prim = prim_base + uint32_t(b);
+                    region[pos++] = make_uint2(id | (prim << 24), (prim >> 8) | tn_bits);
                 }
             } else if (cnt) {
                 spilled = true;                   // region full: void what is left of it, the overflow pass traces the ray

@@ -257,7 +257,7 @@ ARTB_HD int prim_ref_node(const FlatPrim& p) { return p.type == PRIM_MEDIUM ? -1
 // t == t_max) — if it is tested at all: by then t_max is that very t, and every bvh_node between the two leaves' common
 // ancestor and the later leaf first asks its box with it (bvh.cpp:45, aabb.h:25: t_max <= t_min rejects). Replays those
 // box tests with the reference's arithmetic. Rare (coincident faces of adjacent boxes), hence not inlined.
-ARTB_HD_NOINLINE bool tie_later_wins(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim_earlier,
+ARTB_HD bool tie_later_wins(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim_earlier,
                                      uint32_t prim_later)
 {
     if (!s.ref_nodes) return true;
@@ -279,13 +279,19 @@ ARTB_HD_NOINLINE bool tie_later_wins(const SceneView& s, const DRay& world, doub
 // The merge rule, i.e. what hittable_list::hit / bvh_node::hit do by narrowing t_max (hittable_list.cpp:11-15,
 // bvh.cpp:48-49): a candidate replaces the best iff it is closer; at equal t the leaf that comes later in the
 // reference's depth-first order wins, provided the reference would have visited it (tie_later_wins).
+ARTB_HD_NOINLINE bool tie_replaces(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim, uint32_t dfs,
+                                   uint32_t best_prim, uint32_t best_dfs)
+{
+    if (dfs > best_dfs) return tie_later_wins(s, world, t_min, t, best_prim, prim);
+    return !tie_later_wins(s, world, t_min, t, prim, best_prim);
+}
+
 ARTB_HD bool hit_replaces(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim, uint32_t dfs, double best_t,
                           int32_t best_prim, uint32_t best_dfs)
 {
     if (t < best_t || best_prim < 0) return t <= best_t;
     if (t != best_t) return false;
-    if (dfs > best_dfs) return tie_later_wins(s, world, t_min, t, uint32_t(best_prim), prim);
-    return !tie_later_wins(s, world, t_min, t, prim, uint32_t(best_prim));
+    return tie_replaces(s, world, t_min, t, prim, dfs, uint32_t(best_prim), best_dfs);       // rare, out of line
 }
 
 // ---- closest hit ----------------------------------------------------------------------------------
