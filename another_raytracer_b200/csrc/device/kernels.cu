@@ -384,6 +384,7 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
 #define ARTB_REFILL_MIN_IDLE 8        // a warp stops to fetch new rays once this many of its lanes are idle
 #endif
 extern __shared__ uint4 smem_nodes[];
+struct WarpFeed { float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };      // 1 KB per warp
 
 // kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
 // scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared
 k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
     __shared__ uint32_t s_pairs;      // pairs this block has appended to its region
+    __shared__ WarpFeed feeds[(kShared ? ARTB_TRAVERSE_THREADS : 256) / 32];
     const uint32_t n = *io.n_ptr;
     if (!kBatch && blockIdx.x == 0 && threadIdx.x == 0) {
         // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
@@ -428,29 +430,57 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     bool more = true;                 // warp-uniform: the queue may still hold rays
     collect_begin(col, false);
     br.inv[0] = br.inv[1] = br.inv[2] = 1.f; br.c[0] = br.c[1] = br.c[2] = 0.f; br.octinv4 = 0u;
+    // The warp's FEED: 32 rays fetched, converted to their FP32 box-test constants and parked in shared memory by ALL
+    // lanes together (full lane efficiency for the per-ray setup); a lane whose ray ends pops the next one with a
+    // handful of shared loads, so lanes are refilled one by one, at once, while their neighbours keep walking.
+    WarpFeed& feed = feeds[threadIdx.x >> 5];
+    uint32_t feed_count = 0;          // warp-uniform: entries not handed out yet (taken from the top)
     for (;;) {
-        const uint32_t m_active = __ballot_sync(0xffffffffu, active);
-        const uint32_t idle = ~m_active;
-        if ((more && __popc(idle) >= ARTB_REFILL_MIN_IDLE) || m_active == 0u) {
-            if (!more) break;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(io.cursor_traverse, uint32_t(__popc(idle)));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!active) {
-                const uint32_t idx = base + uint32_t(__popc(idle & lt_mask));
-                if (idx < n) {
-                    id = io.list ? io.list[idx] : idx;
-                    const DRay r = trace_io_ray<kBatch>(io, id);
-                    br = make_box_ray(make_trav_ray(r));
+        uint32_t m_active = __ballot_sync(0xffffffffu, active);
+        if (m_active != 0xffffffffu) {
+            if (feed_count == 0u && more) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor_traverse, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t got = base < n ? (n - base < 32u ? n - base : 32u) : 0u;
+                if (uint32_t(lane) < got) {
+                    const uint32_t idx = base + uint32_t(lane);
+                    const uint32_t rid = io.list ? io.list[idx] : idx;
+                    const BoxRay b = make_box_ray(make_trav_ray(trace_io_ray<kBatch>(io, rid)));
+                    feed.inv[0][lane] = b.inv[0]; feed.inv[1][lane] = b.inv[1]; feed.inv[2][lane] = b.inv[2];
+                    feed.c[0][lane] = b.c[0]; feed.c[1][lane] = b.c[1]; feed.c[2][lane] = b.c[2];
+                    feed.octinv4[lane] = b.octinv4;
+                    feed.id[lane] = rid;
+                    store_hit(io.hits.at(rid), io.t_max, -1, 0u);
+                    io.ties.at(rid)->n = 0u;
+                }
+                __syncwarp();
+                feed_count = got;
+                if (base + 32u >= n) more = false;
+            }
+            if (feed_count) {
+                const uint32_t idle = ~m_active;
+                const uint32_t n_idle = uint32_t(__popc(idle));
+                const uint32_t take = n_idle < feed_count ? n_idle : feed_count;
+                const uint32_t rank = uint32_t(__popc(idle & lt_mask));
+                if (!active && rank < take) {
+                    const uint32_t e = feed_count - 1u - rank;
+                    br.inv[0] = feed.inv[0][e]; br.inv[1] = feed.inv[1][e]; br.inv[2] = feed.inv[2][e];
+                    br.c[0] = feed.c[0][e]; br.c[1] = feed.c[1][e]; br.c[2] = feed.c[2][e];
+                    br.octinv4 = feed.octinv4[e];
+                    id = feed.id[e];
                     collect_begin(col, has_tree);
-                    store_hit(io.hits.at(id), io.t_max, -1, 0u);
-                    io.ties.at(id)->n = 0u;
                     active = true;
                     spilled = false;
                 }
+                feed_count -= take;
+                __syncwarp();
+                m_active = __ballot_sync(0xffffffffu, active);
             }
-            if (base + uint32_t(__popc(idle)) >= n) more = false;
-            continue;
+            if (m_active == 0u) {
+                if (feed_count == 0u && !more) break;
+                continue;
+            }
         }
         uint32_t prim_base = 0, prim_mask = 0;
         float tn_min = 0.f;
