@@ -196,10 +196,9 @@ __device__ inline d3 texture_value(const SceneView& s, uint32_t tex, double u, d
 __device__ __forceinline__ d3 sample_unit_sphere(Philox& g)
 {
     const double z = 1.0 - 2.0 * g.next_double();
-    const double phi = 2.0 * ARTB_PI * g.next_double();
     const double rxy = sqrt(fmax(0.0, 1.0 - z * z));
     double sn, cs;
-    sincos(phi, &sn, &cs);
+    sincospi(2.0 * g.next_double(), &sn, &cs);       // the angle in units of pi: no argument reduction by 2*pi
     return mk3(rxy * cs, rxy * sn, z);
 }
 
@@ -212,9 +211,8 @@ __device__ __forceinline__ d3 sample_unit_ball(Philox& g)
 __device__ __forceinline__ void sample_unit_disk(Philox& g, double& x, double& y)
 {
     const double r = sqrt(g.next_double());
-    const double phi = 2.0 * ARTB_PI * g.next_double();
     double sn, cs;
-    sincos(phi, &sn, &cs);
+    sincospi(2.0 * g.next_double(), &sn, &cs);
     x = r * cs; y = r * sn;
 }
 
