@@ -6,14 +6,17 @@
 //   k_shade      one warp = 32 entries of ONE queue: 32 hits of one material type (hit record, texture, emitted,
 //                scatter) or 32 free slots that start the next (pixel, sample): jitter + camera::get_ray. Paths
 //                that end (light, absorbed, depth 50) add their radiance and free the slot; scattered and fresh
-//                rays are queued for the extend kernel
-//   k_extend     closest hit per queued ray (rt_intersect.cuh); misses add the background and free the
-//                slot; hits are binned BY MATERIAL TYPE into per-material queues (warp-aggregated appends)
+//                rays are queued for the closest-hit stage
+//   k_traverse   FP32 walk of the 8-wide tree (in shared memory), emits (ray, primitive) pairs        } the closest
+//   k_pairs      one double-precision primitive test per thread, merged by a 128-bit compare-and-swap  } hit of every
+//   k_finish     global surfaces, media, exact ties; misses add the background and free the slot,     } queued ray
+//                hits are binned BY MATERIAL TYPE into the shade queues (warp-aggregated appends)
+//   (k_extend    the pruned one-phase walk: overflow rays, and scenes whose tree is too big for shared memory)
 //   k_resolve    write_color (color.h:6-22): mean, gamma 2, clamp, 8-bit
 //
-// Path state lives in HBM as three arrays of sector-sized records indexed by slot (ray 64 B, aux 32 B,
-// hit 16 B), so a queue-indexed gather wastes no bytes of a 32 B sector. Two launches per wave on one stream;
-// no kernel waits on another one and the queue counters are reset inside the kernels (see WaveCounters).
+// Path state lives in HBM as ONE 128-byte record per pool slot (ray 64 B | bookkeeping 32 B | hit 16 B | ties 16 B).
+// Five launches per wave on one stream; no kernel waits on the host and the queue counters are reset inside the
+// kernels (see WaveCounters).
 #include "renderer.h"
 #include "rt_shade.cuh"
 #include "bvh_build.cuh"

@@ -38,7 +38,7 @@ struct RenderStats {
     unsigned long long rays = 0;      // closest-hit queries (engine.h:455)
     unsigned long long waves = 0;
     unsigned long long launches = 0;  // kernels launched
-    double extend_ms = 0;             // profile=1: the closest-hit stage (k_traverse + k_confirm + k_extend), per-launch events
+    double extend_ms = 0;             // profile=1: the closest-hit stage (k_traverse + k_pairs + k_finish + k_extend), per-wave events
     double traverse_ms = 0, pairs_ms = 0, finish_ms = 0;
     unsigned long long overflow_rays = 0;   // rays whose candidate list overflowed (traced by the one-phase pass)
     unsigned long long extend_launches = 0;
