@@ -533,6 +533,102 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     if (threadIdx.x == 0) io.pb.region_count[blockIdx.x] = s_pairs < cap ? s_pairs : cap;
 }
 
+// k_walk — the closest TREE hit for scenes whose node array does not fit in shared memory (a million triangles): the
+// pruned, vote-based walk of closest_hit() (trav_round: FP32 box tests, double-precision primitive tests, pruning by the
+// best hit so far — on big trees pruning saves more than the two-phase split gains), but with the per-lane refill of
+// k_traverse: a lane whose ray ends stores its 16-byte result and pops the next ray from the warp's feed, so the warp
+// stays full. The global surfaces, the media and the binning are left to k_finish, exactly as after k_pairs.
+struct WalkFeed { double ray[7][32]; float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };      // 2.75 KB per warp
+#define ARTB_WALK_THREADS 128
+template <bool kBatch>
+__global__ void __launch_bounds__(ARTB_WALK_THREADS, 4)
+k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
+{
+    __shared__ WalkFeed feeds[ARTB_WALK_THREADS / 32];
+    const uint32_t n = *io.n_ptr;
+    if (!kBatch && blockIdx.x == 0 && threadIdx.x == 0) {
+        // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
+        const unsigned long long left = c->total - c->issued;
+        const unsigned long long nr = c->n_out[cur ^ 1][Q_REGEN];
+        c->issued += nr < left ? nr : left;
+        c->n_out[cur ^ 1][Q_REGEN] = 0;
+        c->rays += n;
+    }
+    if (n == 0) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool has_tree = s.n_world_prims > s.n_global_prims;
+    const float t_min_f = d2f_rd(io.t_min);
+    WalkFeed& feed = feeds[threadIdx.x >> 5];
+    uint32_t feed_count = 0;          // warp-uniform
+    bool more = true;                 // warp-uniform
+    uint2 stack[ARTB_STACK_DEPTH];
+    Traversal tv;
+    trav_begin(tv, io.t_max, false);
+    tv.alive = false;
+    DRay ray;
+    ray.o = mk3(0, 0, 0); ray.d = mk3(1, 0, 0); ray.tm = 0;
+    BoxRay br = make_box_ray(ray);
+    uint32_t id = 0;
+    bool has = false;                 // this lane holds a ray whose result is not stored yet
+    for (;;) {
+        uint32_t m_alive = __ballot_sync(0xffffffffu, tv.alive);
+        if (m_alive != 0xffffffffu) {
+            if (has && !tv.alive) {
+                store_hit(io.hits.at(id), tv.best.t, tv.best.prim, tv.best.dfs);
+                has = false;
+            }
+            if (feed_count == 0u && more) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor_traverse, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t got = base < n ? (n - base < 32u ? n - base : 32u) : 0u;
+                if (uint32_t(lane) < got) {
+                    const uint32_t idx = base + uint32_t(lane);
+                    const uint32_t rid = io.list ? io.list[idx] : idx;
+                    const DRay r = trace_io_ray<kBatch>(io, rid);
+                    const BoxRay b = make_box_ray(r);
+                    feed.ray[0][lane] = r.o.x; feed.ray[1][lane] = r.o.y; feed.ray[2][lane] = r.o.z;
+                    feed.ray[3][lane] = r.d.x; feed.ray[4][lane] = r.d.y; feed.ray[5][lane] = r.d.z; feed.ray[6][lane] = r.tm;
+                    feed.inv[0][lane] = b.inv[0]; feed.inv[1][lane] = b.inv[1]; feed.inv[2][lane] = b.inv[2];
+                    feed.c[0][lane] = b.c[0]; feed.c[1][lane] = b.c[1]; feed.c[2][lane] = b.c[2];
+                    feed.octinv4[lane] = b.octinv4;
+                    feed.id[lane] = rid;
+                }
+                __syncwarp();
+                feed_count = got;
+                if (base + 32u >= n) more = false;
+            }
+            if (feed_count) {
+                const uint32_t idle = ~m_alive;
+                const uint32_t n_idle = uint32_t(__popc(idle));
+                const uint32_t take = n_idle < feed_count ? n_idle : feed_count;
+                const uint32_t rank = uint32_t(__popc(idle & lt_mask));
+                if (!tv.alive && rank < take) {
+                    const uint32_t e = feed_count - 1u - rank;
+                    ray.o = mk3(feed.ray[0][e], feed.ray[1][e], feed.ray[2][e]);
+                    ray.d = mk3(feed.ray[3][e], feed.ray[4][e], feed.ray[5][e]);
+                    ray.tm = feed.ray[6][e];
+                    br.inv[0] = feed.inv[0][e]; br.inv[1] = feed.inv[1][e]; br.inv[2] = feed.inv[2][e];
+                    br.c[0] = feed.c[0][e]; br.c[1] = feed.c[1][e]; br.c[2] = feed.c[2][e];
+                    br.octinv4 = feed.octinv4[e];
+                    id = feed.id[e];
+                    trav_begin(tv, io.t_max, has_tree);
+                    has = true;
+                }
+                feed_count -= take;
+                __syncwarp();
+                m_alive = __ballot_sync(0xffffffffu, tv.alive);
+            }
+            if (m_alive == 0u) {
+                if (feed_count == 0u && !more) break;
+                continue;
+            }
+        }
+        trav_round(s, s.nodes, 0xffffffffu, tv, stack, ray, br, io.t_min, t_min_f, nullptr);
+    }
+}
+
 #ifndef ARTB_PAIRS_THREADS
 #define ARTB_PAIRS_THREADS 64         // small blocks: the three barriers of the tile sort stall fewer warps (measured -4 %)
 #endif
@@ -1478,6 +1574,8 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     bool two_phase = I.nodes_fit_shared(view_);
     if (const char* e = getenv("ARTB_TWO_PHASE")) two_phase = atoi(e) != 0;
     if (w.pool >= ARTB_PAIR_MAX_ID || view_.n_prims >= ARTB_PAIR_MAX_ID) two_phase = false;     // pack_pair: 24-bit ids
+    bool use_walk = true;               // big trees: k_walk + k_finish; ARTB_WALK=0 falls back to the chunked k_extend
+    if (const char* e = getenv("ARTB_WALK")) use_walk = atoi(e) != 0;
     RenderStats S;
     cudaEvent_t ev_begin, ev_end;
     CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
@@ -1495,7 +1593,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
             float ms = 0.f;
             CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k], I.ev[5 * k + 4]));
             S.extend_ms += ms;
-            if (two_phase) {
+            {   // k_traverse (or k_walk) | k_pairs | k_finish; all three events are recorded in every mode
                 CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k], I.ev[5 * k + 1]));
                 S.traverse_ms += ms;
                 CUDA_CHECK(cudaEventElapsedTime(&ms, I.ev[5 * k + 1], I.ev[5 * k + 2]));
@@ -1541,7 +1639,20 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr);
                     k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);
                     S.launches += 5;
+                } else if (use_walk) {
+                    TraceIO io{};
+                    io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits; io.ties = w.ties;
+                    io.cursor_traverse = &w.c->cursor[0];
+                    io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
+                    io.t_min = 0.001; io.t_max = INFINITY;
+                    io.rays = w.rays; io.aux = w.aux;
+                    k_walk<false><<<I.sm_count * 4, ARTB_WALK_THREADS, 0, st>>>(io, view_, w.c, cur);
+                    if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 1], st)); CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 2], st)); }
+                    k_finish<false><<<I.sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view_, w, rp, cur);
+                    if (profile) CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 3], st));
+                    S.launches += 3;
                 } else {
+                    if (profile) for (int e = 1; e <= 3; ++e) CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + e], st));
                     k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 1);
                     S.launches += 2;
                 }
