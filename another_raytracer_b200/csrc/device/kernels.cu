@@ -664,6 +664,16 @@ k_pairs(TraceIO io, SceneView s)
             const uint32_t i = t0 + uint32_t(k) * ARTB_PAIRS_THREADS + threadIdx.x;
             pr[k] = i < cnt ? region[i] : make_uint2(0xffffffffu, 0u);
         }
+        // hit-aware culling: the ray enters this primitive's leaf box no earlier than tn; if its record already holds a
+        // closer hit (merged by pairs processed before — nearer leaves are emitted, hence processed, earlier) the pair
+        // cannot win and nothing is loaded or tested for it. The record loads also warm the rays' lines; all of a
+        // thread's loads are issued before the first one is looked at.
+        unsigned long long rec_lo[ARTB_PAIRS_PER_THREAD], rec_hi[ARTB_PAIRS_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
+            rec_lo[k] = 0; rec_hi[k] = 0;
+            if (pr[k].x != 0xffffffffu) peek_hit(io.hits.at(pr[k].x & 0xffffffu), rec_lo[k], rec_hi[k]);
+        }
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             uint32_t cls = ARTB_PRIM_CLASSES;
@@ -671,13 +681,8 @@ k_pairs(TraceIO io, SceneView s)
                 uint32_t ray, prim;
                 float tn;
                 unpack_pair(pr[k], ray, prim, tn);
-                // hit-aware culling: the ray enters this primitive's leaf box no earlier than tn; if its record already
-                // holds a closer hit (merged by pairs processed before — nearer leaves are emitted, hence processed,
-                // earlier) the pair cannot win and nothing is loaded or tested for it. The load also warms the ray's line.
-                unsigned long long lo, hi;
-                peek_hit(io.hits.at(ray), lo, hi);
-                const int32_t cur_prim = int32_t(uint32_t(hi));
-                const bool culled = cur_prim == ARTB_HIT_OVERFLOW || (cur_prim >= 0 && double(tn) > __longlong_as_double((long long)lo));
+                const int32_t cur_prim = int32_t(uint32_t(rec_hi[k]));
+                const bool culled = cur_prim == ARTB_HIT_OVERFLOW || (cur_prim >= 0 && double(tn) > __longlong_as_double((long long)rec_lo[k]));
                 if (!culled) cls = s.prim_class[prim];
             }
             cls_rank[k] = (cls << 24) | atomicAdd(&class_count[cls], 1u);
