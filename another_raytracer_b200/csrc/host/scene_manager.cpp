@@ -27,7 +27,7 @@ std::string assets_root()
 }
 
 // reference: scene_manager.cpp:13-64
-hittable_list scene_manager::_random_scene()
+static hittable_list build_random_spheres()
 {
     hittable_list objects;
 
@@ -70,7 +70,7 @@ hittable_list scene_manager::_random_scene()
 }
 
 // reference: scene_manager.cpp:66-76
-hittable_list scene_manager::_two_spheres()
+static hittable_list build_two_spheres()
 {
     hittable_list objects;
     auto checker = mk<checker_texture>(color(0.2, 0.3, 0.1), color(0.9, 0.9, 0.9));
@@ -80,7 +80,7 @@ hittable_list scene_manager::_two_spheres()
 }
 
 // reference: scene_manager.cpp:78-87
-hittable_list scene_manager::_two_perlin_spheres()
+static hittable_list build_two_perlin_spheres()
 {
     hittable_list objects;
     auto pertext = mk<noise_texture>(4);
@@ -90,7 +90,7 @@ hittable_list scene_manager::_two_perlin_spheres()
 }
 
 // reference: scene_manager.cpp:89-96
-hittable_list scene_manager::_earth()
+static hittable_list build_earth()
 {
     auto earth_texture = mk<image_texture>(assets_root() + "/textures/earthmap.png");
     auto globe = mk<sphere>(point3(0, 0, 0), 2, mk<lambertian>(earth_texture));
@@ -98,7 +98,7 @@ hittable_list scene_manager::_earth()
 }
 
 // reference: scene_manager.cpp:98-110
-hittable_list scene_manager::_simple_light()
+static hittable_list build_simple_light()
 {
     hittable_list objects;
     auto pertext = mk<noise_texture>(4);
@@ -120,7 +120,7 @@ std::shared_ptr<hittable> placed_box(const point3& extent, double degrees, const
 } // namespace
 
 // reference: scene_manager.cpp:112-139
-hittable_list scene_manager::_cornell_box()
+static hittable_list build_cornell_box()
 {
     hittable_list objects;
     auto red = mk<lambertian>(color(.65, .05, .05));
@@ -141,7 +141,7 @@ hittable_list scene_manager::_cornell_box()
 }
 
 // reference: scene_manager.cpp:141-169 (note the swapped floor/ceiling order w.r.t. _cornell_box)
-hittable_list scene_manager::_cornell_smoke()
+static hittable_list build_cornell_smoke()
 {
     hittable_list objects;
     auto red = mk<lambertian>(color(.65, .05, .05));
@@ -164,7 +164,7 @@ hittable_list scene_manager::_cornell_smoke()
 }
 
 // reference: scene_manager.cpp:171-234
-hittable_list scene_manager::_final_scene()
+static hittable_list build_next_week_final()
 {
     hittable_list boxes1;
     auto ground = mk<lambertian>(color(0.48, 0.83, 0.53));
@@ -219,7 +219,7 @@ hittable_list scene_manager::_final_scene()
 }
 
 // reference: scene_manager.cpp:236-258
-hittable_list scene_manager::_mesh_scene(const std::string& obj_path)
+static hittable_list build_mesh_scene(const std::string& obj_path, bool mesh_as_soup)
 {
     mesh m;
     if (!m.parse(obj_path)) throw std::logic_error("cannot parse input obj file!");
@@ -239,7 +239,7 @@ hittable_list scene_manager::_mesh_scene(const std::string& obj_path)
 
 // NEW — BASELINE.json config 5: a closed-form height field, no RNG involved.
 // side x side vertices on [-12,12]^2, y = sum of three sine products; 2*(side-1)^2 triangles.
-hittable_list scene_manager::_heightfield_scene()
+static hittable_list build_heightfield(int heightfield_side)
 {
     const int n = heightfield_side;
     if (n < 2) throw std::logic_error("heightfield_side must be >= 2");
@@ -281,7 +281,7 @@ scene scene_manager::build(scene_alias alias)
 
     switch (alias) {
         case scene_alias::random:
-            world.objects = _random_scene();
+            world.objects = build_random_spheres();
             world.background = sky;
             world.lookfrom = point3(13, 2, 3);
             world.lookat = point3(0, 0, 0);
@@ -289,77 +289,77 @@ scene scene_manager::build(scene_alias alias)
             world.aperture = 0.1;
             break;
         case scene_alias::two_spheres:
-            world.objects = _two_spheres();
+            world.objects = build_two_spheres();
             world.background = sky;
             world.lookfrom = point3(13, 2, 3);
             world.lookat = point3(0, 0, 0);
             world.vfov = 20.0;
             break;
         case scene_alias::two_perlin_spheres:
-            world.objects = _two_perlin_spheres();
+            world.objects = build_two_perlin_spheres();
             world.background = sky;
             world.lookfrom = point3(13, 2, 3);
             world.lookat = point3(0, 0, 0);
             world.vfov = 20.0;
             break;
         case scene_alias::earth:
-            world.objects = _earth();
+            world.objects = build_earth();
             world.background = sky;
             world.lookfrom = point3(13, 2, 3);
             world.lookat = point3(0, 0, 0);
             world.vfov = 20.0;
             break;
         case scene_alias::simple_light:
-            world.objects = _simple_light();
+            world.objects = build_simple_light();
             world.background = color(0, 0, 0);
             world.lookfrom = point3(26, 3, 6);
             world.lookat = point3(0, 2, 0);
             world.vfov = 20.0;
             break;
         case scene_alias::cornell_box:
-            world.objects = _cornell_box();
+            world.objects = build_cornell_box();
             world.background = color(0, 0, 0);
             world.lookfrom = point3(278, 278, -800);
             world.lookat = point3(278, 278, 0);
             world.vfov = 40.0;
             break;
         case scene_alias::cornell_smoke:
-            world.objects = _cornell_smoke();
+            world.objects = build_cornell_smoke();
             world.background = color(0, 0, 0);
             world.lookfrom = point3(278, 278, -800);
             world.lookat = point3(278, 278, 0);
             world.vfov = 40.0;
             break;
         case scene_alias::final:
-            world.objects = _final_scene();
+            world.objects = build_next_week_final();
             world.background = color(0, 0, 0);
             world.lookfrom = point3(478, 278, -600);
             world.lookat = point3(278, 278, 0);
             world.vfov = 40.0;
             break;
         case scene_alias::mesh:
-            world.objects = _mesh_scene(assets_root() + "/models/capsule/capsule.obj");
+            world.objects = build_mesh_scene(assets_root() + "/models/capsule/capsule.obj", mesh_as_soup);
             world.background = sky;
             world.lookfrom = point3(2, 2, 1);
             world.lookat = point3(0, 0, 0);
             world.vfov = 75.0;
             break;
         case scene_alias::cow:
-            world.objects = _mesh_scene(assets_root() + "/models/cow.obj");
+            world.objects = build_mesh_scene(assets_root() + "/models/cow.obj", mesh_as_soup);
             world.background = sky;
             world.lookfrom = point3(4, 2, 6);
             world.lookat = point3(2, 0, 0);
             world.vfov = 75.0;
             break;
         case scene_alias::dino:
-            world.objects = _mesh_scene(assets_root() + "/models/dino.obj");
+            world.objects = build_mesh_scene(assets_root() + "/models/dino.obj", mesh_as_soup);
             world.background = sky;
             world.lookfrom = point3(0, 15, 25);
             world.lookat = point3(0, 10, 0);
             world.vfov = 75.0;
             break;
         case scene_alias::heightfield:
-            world.objects = _heightfield_scene();
+            world.objects = build_heightfield(heightfield_side);
             world.background = sky;
             world.lookfrom = point3(0, 7, 19);
             world.lookat = point3(0, 0.3, 0);

@@ -47,24 +47,15 @@ enum class scene_alias {
 std::string assets_root();
 void set_assets_root(const std::string& path);
 
+// scene_manager::build is the reference's entry point (scene_manager.h:29-44); the per-scene builders are file-local
+// functions of scene_manager.cpp.
 class scene_manager {
 public:
-    scene build(scene_alias alias);
+    // options the reference hard-codes
+    bool mesh_as_soup = false;        // aliases 9-11: emit one triangle_soup instead of per-triangle objects
+    int heightfield_side = 708;       // alias 12: vertices per side
 
-    // NEW: options the reference hard-codes
-    bool mesh_as_soup = false;        // cow/dino/mesh: emit one triangle_soup instead of per-triangle objects
-    int heightfield_side = 708;       // vertices per side of alias 12
-private:
-    hittable_list _random_scene();
-    hittable_list _two_spheres();
-    hittable_list _two_perlin_spheres();
-    hittable_list _earth();
-    hittable_list _simple_light();
-    hittable_list _cornell_box();
-    hittable_list _cornell_smoke();
-    hittable_list _final_scene();
-    hittable_list _mesh_scene(const std::string& obj_path);
-    hittable_list _heightfield_scene();
+    scene build(scene_alias alias);
 };
 
 } // namespace artb
