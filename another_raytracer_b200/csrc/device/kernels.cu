@@ -24,6 +24,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -1072,6 +1073,29 @@ __global__ void k_adaptive_update(WaveCounters* c, const uint32_t* list, uint32_
     }
 }
 
+// Partition B (tile split): the pixels of the tiles t = ty*tiles_x + tx with t % parts == part, tile by tile (row-major
+// inside a tile). One block per owned tile; offsets[k] = pixels of the owned tiles before the k-th one (a few thousand
+// numbers, prefix-summed on the host once per (size, tiling, part) and cached with the list).
+__global__ void k_tile_list(uint32_t* list, const uint32_t* offsets, int width, int height, int ts, int parts, int part)
+{
+    const int tiles_x = (width + ts - 1) / ts;
+    const int t = part + int(blockIdx.x) * parts;
+    const int ty = t / tiles_x, tx = t % tiles_x;
+    const int w = (width - tx * ts < ts ? width - tx * ts : ts), h = (height - ty * ts < ts ? height - ty * ts : ts);
+    const uint32_t offset = offsets[blockIdx.x];
+    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
+        const int x = tx * ts + i % w, y = ty * ts + i / w;
+        list[offset + uint32_t(i)] = uint32_t(y) * uint32_t(width) + uint32_t(x);
+    }
+}
+
+// fixed-spp rendering: every listed pixel received exactly `spp` samples (the count buffer of include/artb.h)
+__global__ void k_count_fixed(const uint32_t* list, uint32_t n, uint32_t spp, uint32_t* count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) count[list ? list[i] : i] += spp;
+}
+
 __global__ void k_resolve(const float* accum, const uint32_t* count, int n_pixels, int fixed_spp, uint8_t* rgb)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1086,32 +1110,42 @@ __global__ void k_resolve(const float* accum, const uint32_t* count, int n_pixel
     }
 }
 
-// one-phase walk over explicit rays: the overflow pass of the batch path (list = the flagged ray indices)
-__global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* rays, const uint32_t* list, uint64_t n,
-                                                     double t_min, double t_max, const double* xi, HitRecordOut* out)
+// one-phase walk over explicit rays: the overflow pass of the batch path (list = the flagged ray indices, their number
+// read from device memory: nothing waits on the host) and the path of scenes whose ids do not fit pack_pair
+__global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* rays, const uint32_t* list, uint64_t n_fixed,
+                                                     const uint32_t* n_ptr, unsigned long long* n_total, double t_min, double t_max,
+                                                     const double* xi, HitRecordOut* out)
 {
-    const uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint64_t i = list ? list[j] : j;
-    DRay r;
-    r.o = ld3(rays + i * 7); r.d = ld3(rays + i * 7 + 3); r.tm = rays[i * 7 + 6];
-    MediumXi mx;
-    mx.row = xi ? xi + i * s.n_media : nullptr;
-    mx.seed = 0; mx.stream = 0; mx.path_lo = uint32_t(i); mx.path_hi = uint32_t(i >> 32); mx.bounce = 0;
-    const ClosestHit h = closest_hit(s, s.nodes, r, t_min, t_max, mx);
-    HitRecordOut o;
-    if (h.prim < 0) {
-        o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
-        o.t = o.u = o.v = 0; o.p[0] = o.p[1] = o.p[2] = 0; o.normal[0] = o.normal[1] = o.normal[2] = 0;
-    } else {
-        const HitInfo hi = make_hit_info(s, h.prim, r, h.t);
-        o.hit = 1; o.prim_id = int32_t(h.dfs); o.front_face = hi.front_face ? 1 : 0;
-        o.material_type = int32_t(s.materials[hi.material].type);
-        o.t = hi.t; o.u = hi.u; o.v = hi.v;
-        o.p[0] = hi.p.x; o.p[1] = hi.p.y; o.p[2] = hi.p.z;
-        o.normal[0] = hi.normal.x; o.normal[1] = hi.normal.y; o.normal[2] = hi.normal.z;
+    const uint64_t n = n_ptr ? uint64_t(*n_ptr) : n_fixed;
+    if (n_total && blockIdx.x == 0 && threadIdx.x == 0) *n_total += n;
+    for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += uint64_t(gridDim.x) * blockDim.x) {
+        const uint64_t i = list ? list[j] : j;
+        DRay r;
+        r.o = ld3(rays + i * 7); r.d = ld3(rays + i * 7 + 3); r.tm = rays[i * 7 + 6];
+        MediumXi mx;
+        mx.row = xi ? xi + i * s.n_media : nullptr;
+        mx.seed = 0; mx.stream = 0; mx.path_lo = uint32_t(i); mx.path_hi = uint32_t(i >> 32); mx.bounce = 0;
+        const ClosestHit h = closest_hit(s, s.nodes, r, t_min, t_max, mx);
+        HitRecordOut o;
+        if (h.prim < 0) {
+            o.hit = 0; o.prim_id = -1; o.front_face = 0; o.material_type = -1;
+            o.t = o.u = o.v = 0; o.p[0] = o.p[1] = o.p[2] = 0; o.normal[0] = o.normal[1] = o.normal[2] = 0;
+        } else {
+            const HitInfo hi = make_hit_info(s, h.prim, r, h.t);
+            o.hit = 1; o.prim_id = int32_t(h.dfs); o.front_face = hi.front_face ? 1 : 0;
+            o.material_type = int32_t(s.materials[hi.material].type);
+            o.t = hi.t; o.u = hi.u; o.v = hi.v;
+            o.p[0] = hi.p.x; o.p[1] = hi.p.y; o.p[2] = hi.p.z;
+            o.normal[0] = hi.normal.x; o.normal[1] = hi.normal.y; o.normal[2] = hi.normal.z;
+        }
+        out[i] = o;
     }
-    out[i] = o;
+}
+
+// counters of one chunk of artb_trace_batch: {n, traverse cursor, -, overflow count}
+__global__ void k_batch_counters(uint32_t* ctr, uint32_t n)
+{
+    ctr[0] = n; ctr[1] = 0u; ctr[2] = 0u; ctr[3] = 0u;
 }
 
 // =====================================================================================================
@@ -1133,10 +1167,22 @@ struct Renderer::Impl {
     // adaptive scratch
     uint32_t* list[2] = { nullptr, nullptr };
     uint32_t* tile_list = nullptr;
+    int tile_key[5] = { 0, 0, 0, 0, -1 };         // width, height, tile size, parts, part of the list held in tile_list
+    size_t tile_count = 0;
+    uint32_t* tile_offsets = nullptr;
+    size_t tile_offsets_capacity = 0;
     float* lumsq = nullptr;
     size_t list_capacity = 0;
     // event pool for per-kernel timing
     std::vector<cudaEvent_t> ev;
+    // scratch of trace_batch_device (grow-only: the hook is also what "Mrays/s on fixed batches" is measured with)
+    struct BatchScratch {
+        std::vector<void*> bag;
+        PathHit* hits = nullptr; PathTie* ties = nullptr; uint2* pairs = nullptr; uint32_t* region_count = nullptr;
+        uint32_t* overflow = nullptr; uint32_t* ctr = nullptr; unsigned long long* overflow_total = nullptr;
+        uint64_t cap = 0; size_t pair_capacity = 0;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+    } batch;
 
     // launch helpers shared by the renderer and the batch path. The tree walk runs in shared memory when the node
     // array fits; its grid decides how many regions the pair buffer is cut into.
@@ -1151,10 +1197,20 @@ struct Renderer::Impl {
         io.pb.n_regions = nodes_fit_shared(view) ? uint32_t(sm_count) * ARTB_TRAVERSE_GRID_PER_SM : uint32_t(sm_count) * 6u;
         io.pb.region_cap = uint32_t(std::min<size_t>(capacity / io.pb.n_regions, 0x7fffffffu));
     }
+    // two_phase: k_traverse + k_pairs + k_finish; otherwise the pruned walk k_walk + k_finish (trees beyond shared memory).
+    // ev (optional): three events recorded after the tree kernel, after k_pairs (at once in walk mode) and after k_finish.
     template <bool kBatch>
     void launch_trace(const SceneView& view, const TraceIO& io, const WaveBuffers& w, const RoundParams& rp, int cur, cudaStream_t st,
-                      cudaEvent_t* ev)
+                      cudaEvent_t* ev, bool two_phase)
     {
+        if (!two_phase) {
+            k_walk<kBatch><<<sm_count * 4, ARTB_WALK_THREADS, 0, st>>>(io, view, w.c, cur);
+            if (ev) { CUDA_CHECK(cudaEventRecord(ev[0], st)); CUDA_CHECK(cudaEventRecord(ev[1], st)); }
+            k_finish<kBatch><<<sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+            if (ev) CUDA_CHECK(cudaEventRecord(ev[2], st));
+            CUDA_CHECK(cudaGetLastError());
+            return;
+        }
         const size_t node_bytes = std::max<size_t>(size_t(view.n_nodes) * sizeof(FlatNode8), 16);
         if (nodes_fit_shared(view)) {
             if (node_bytes > traverse_smem_set[kBatch]) {
@@ -1195,12 +1251,22 @@ static const T* dev_upload(std::vector<void*>& bag, const std::vector<T>& v, cud
 
 Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(device)
 {
+    // a constructor that throws does not run the destructor: release what was acquired so far here
+    try {
+        init(pool_paths);
+    } catch (...) {
+        release();
+        throw;
+    }
+}
+
+void Renderer::init(uint32_t pool_paths)
+{
+    const int device = device_;
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
-    if (e != cudaSuccess || n_dev == 0) {
-        delete impl_;
-        throw std::runtime_error("no CUDA device: this backend has no CPU fallback");
-    }
+    if (e != cudaSuccess || n_dev == 0) throw std::runtime_error("no CUDA device: this backend has no CPU fallback");
+    if (device < 0 || device >= n_dev) throw std::runtime_error("CUDA device ordinal out of range");
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -1234,35 +1300,50 @@ Renderer::Renderer(int device, uint32_t pool_paths) : impl_(new Impl), device_(d
     CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
 }
 
-Renderer::~Renderer()
+Renderer::~Renderer() { release(); }
+
+void Renderer::release()
 {
+    if (!impl_) return;
     cudaSetDevice(device_);
     cudaDeviceSynchronize();
     for (void* p : impl_->scene_allocs) cudaFree(p);
     for (void* p : impl_->pool_allocs) cudaFree(p);
     if (impl_->list[0]) cudaFree(impl_->list[0]);
     if (impl_->list[1]) cudaFree(impl_->list[1]);
-    if (impl_->tile_list) cudaFree(impl_->tile_list);
     if (impl_->lumsq) cudaFree(impl_->lumsq);
     if (impl_->host_accum) cudaFree(impl_->host_accum);
     if (impl_->host_count) cudaFree(impl_->host_count);
     if (impl_->host_rgb) cudaFree(impl_->host_rgb);
     if (impl_->counters_host) cudaFreeHost(impl_->counters_host);
+    for (void* p : impl_->batch.bag) cudaFree(p);
+    if (impl_->batch.e0) cudaEventDestroy(impl_->batch.e0);
+    if (impl_->batch.e1) cudaEventDestroy(impl_->batch.e1);
     for (cudaEvent_t e : impl_->ev) cudaEventDestroy(e);
+    if (impl_->tile_list) cudaFree(impl_->tile_list);
+    if (impl_->tile_offsets) cudaFree(impl_->tile_offsets);
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+    stream_ = nullptr;
     delete impl_;
+    impl_ = nullptr;
 }
 
 void Renderer::upload(const FlatScene& fs)
 {
     CUDA_CHECK(cudaSetDevice(device_));
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    // everything that can be rejected is rejected BEFORE the previous scene is touched ...
+    if (fs.bvh_depth > ARTB_MAX_BVH8_DEPTH)
+        throw std::runtime_error("scene BVH is deeper than the device traversal stack");
     CUDA_CHECK(cudaStreamSynchronize(st));
+    // ... and from here on there is no scene until the new one is complete: a failing allocation / copy / device build
+    // must not leave has_scene_ pointing at freed arrays
+    has_scene_ = false;
+    view_ = SceneView{};
+    scene_bytes_ = 0;
     for (void* p : impl_->scene_allocs) cudaFree(p);
     impl_->scene_allocs.clear();
     last_build_ = BvhBuildStats{};
-    if (fs.bvh_depth > ARTB_MAX_BVH8_DEPTH)
-        throw std::runtime_error("scene BVH is deeper than the device traversal stack");
     uint64_t bytes = 0;
     SceneView v{};
     v.prims = dev_upload(impl_->scene_allocs, fs.prims, st, bytes);
@@ -1297,9 +1378,18 @@ void Renderer::upload(const FlatScene& fs)
     view_ = v;
     scene_bytes_ = bytes;
     has_scene_ = true;
+    max_dfs_id_ = 0;
+    for (uint32_t i = 0; i < fs.n_world_prims; ++i) max_dfs_id_ = std::max(max_dfs_id_, fs.prims[i].dfs_id);
     // a flat scene that arrives without a tree (FlattenOptions::device_bvh, or a foreign host that has none) gets
     // one built here, on the device
-    if (fs.nodes.empty() && fs.n_world_prims > fs.n_global_prims) build_bvh_device(fs.device_bvh_leaf_prims, &last_build_);
+    if (fs.nodes.empty() && fs.n_world_prims > fs.n_global_prims) {
+        try {
+            build_bvh_device(fs.device_bvh_leaf_prims, &last_build_);
+        } catch (...) {
+            has_scene_ = false;          // primitives without a tree cannot be rendered
+            throw;
+        }
+    }
 }
 
 float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_min, double t_max, const double* xi_dev,
@@ -1309,68 +1399,61 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
     CUDA_CHECK(cudaSetDevice(device_));
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (n == 0) return 0.f;
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    std::vector<void*> bag;
-    float ms = 0.f;
-    try {
-        const uint64_t kChunk = 1u << 22;                         // rays per pass
-        const uint64_t cap = std::min<uint64_t>(n, kChunk);
-        size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
-        if (const char* e = getenv("ARTB_PAIR_CAPACITY")) pair_capacity = std::max<size_t>(size_t(atoll(e)), 1);
-        PathHit* hits = dev_alloc<PathHit>(bag, cap);
-        PathTie* ties = dev_alloc<PathTie>(bag, cap);
-        uint2* pairs = dev_alloc<uint2>(bag, pair_capacity);
-        uint32_t* region_count = dev_alloc<uint32_t>(bag, ARTB_MAX_REGIONS);
-        uint32_t* overflow = dev_alloc<uint32_t>(bag, cap);
-        uint32_t* ctr = dev_alloc<uint32_t>(bag, 4);              // n, traverse cursor, -, overflow count
-        last_trace_overflow_ = 0;
-        CUDA_CHECK(cudaEventRecord(e0, st));
-        if (view_.n_prims >= ARTB_PAIR_MAX_ID) {                  // pack_pair holds 24-bit ids: such scenes take the one-phase walk
-            for (uint64_t first = 0; first < n; first += kChunk) {
-                const uint64_t m = std::min<uint64_t>(kChunk, n - first);
-                k_trace_batch<<<unsigned((m + 127) / 128), 128, 0, st>>>(view_, rays_dev + first * 7, nullptr, m, t_min, t_max,
-                                                                         xi_dev ? xi_dev + first * view_.n_media : nullptr, out_dev + first);
-            }
-            CUDA_CHECK(cudaGetLastError());
-            last_trace_overflow_ = n;
-            n = 0;
-        }
-        for (uint64_t first = 0; first < n; first += kChunk) {
-            const uint32_t m = uint32_t(std::min<uint64_t>(kChunk, n - first));
-            const uint32_t init[4] = { m, 0u, 0u, 0u };
-            CUDA_CHECK(cudaMemcpyAsync(ctr, init, sizeof(init), cudaMemcpyHostToDevice, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));               // `init` lives on this stack frame
-            TraceIO io{};
-            io.n_ptr = ctr; io.list = nullptr; io.hits = { reinterpret_cast<char*>(hits), uint32_t(sizeof(PathHit)) };
-            io.ties = { reinterpret_cast<char*>(ties), uint32_t(sizeof(PathTie)) };
-            impl_->set_pair_buffer(view_, io, pairs, pair_capacity, region_count);
-            io.cursor_traverse = ctr + 1; io.q_overflow = overflow; io.n_overflow = ctr + 3;
-            io.t_min = t_min; io.t_max = t_max;
-            io.batch_rays = rays_dev + first * 7;
-            io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
-            io.batch_out = out_dev + first;
-            impl_->launch_trace<true>(view_, io, impl_->wb, RoundParams{}, 0, st, nullptr);
-            uint32_t n_over = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&n_over, ctr + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
-            last_trace_overflow_ += n_over;
-            if (n_over) {
-                k_trace_batch<<<(n_over + 127) / 128, 128, 0, st>>>(view_, io.batch_rays, overflow, n_over, t_min, t_max, io.batch_xi,
-                                                                    io.batch_out);
-                CUDA_CHECK(cudaGetLastError());
-            }
-        }
-        CUDA_CHECK(cudaEventRecord(e1, st));
+    Impl& I = *impl_;
+    Impl::BatchScratch& B = I.batch;
+    const uint64_t kChunk = 1u << 22;                         // rays per pass
+    const uint64_t cap = std::min<uint64_t>(n, kChunk);
+    size_t pair_capacity = std::max<size_t>(size_t(cap) * ARTB_PAIRS_PER_RAY, size_t(ARTB_MAX_REGIONS) * 8192);
+    if (const char* e = getenv("ARTB_PAIR_CAPACITY")) pair_capacity = std::max<size_t>(size_t(atoll(e)), 1);
+    if (!B.e0) { CUDA_CHECK(cudaEventCreate(&B.e0)); CUDA_CHECK(cudaEventCreate(&B.e1)); }
+    if (B.cap < cap || B.pair_capacity != pair_capacity) {
         CUDA_CHECK(cudaStreamSynchronize(st));
-        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    } catch (...) {
-        for (void* p : bag) cudaFree(p);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        throw;
+        for (void* p : B.bag) cudaFree(p);
+        B.bag.clear();
+        const uint64_t want = std::max(cap, B.cap);
+        B.cap = 0; B.pair_capacity = 0;
+        B.hits = dev_alloc<PathHit>(B.bag, want);
+        B.ties = dev_alloc<PathTie>(B.bag, want);
+        B.pairs = dev_alloc<uint2>(B.bag, pair_capacity);
+        B.region_count = dev_alloc<uint32_t>(B.bag, ARTB_MAX_REGIONS);
+        B.overflow = dev_alloc<uint32_t>(B.bag, want);
+        B.ctr = dev_alloc<uint32_t>(B.bag, 4);
+        B.overflow_total = dev_alloc<unsigned long long>(B.bag, 1);
+        B.cap = want; B.pair_capacity = pair_capacity;
     }
-    for (void* p : bag) cudaFree(p);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    // the pair kernels when the tree fits in shared memory, else the pruned walk — the choice render_device makes
+    bool two_phase = I.nodes_fit_shared(view_);
+    if (const char* e = getenv("ARTB_TWO_PHASE")) two_phase = atoi(e) != 0;
+    const bool ids_fit = view_.n_prims < ARTB_PAIR_MAX_ID;     // pack_pair holds 24-bit ids
+    if (!ids_fit) two_phase = false;
+    last_trace_overflow_ = 0;
+    CUDA_CHECK(cudaMemsetAsync(B.overflow_total, 0, sizeof(unsigned long long), st));
+    CUDA_CHECK(cudaEventRecord(B.e0, st));
+    for (uint64_t first = 0; first < n; first += kChunk) {
+        const uint32_t m = uint32_t(std::min<uint64_t>(kChunk, n - first));
+        k_batch_counters<<<1, 1, 0, st>>>(B.ctr, m);
+        TraceIO io{};
+        io.n_ptr = B.ctr; io.list = nullptr; io.hits = { reinterpret_cast<char*>(B.hits), uint32_t(sizeof(PathHit)) };
+        io.ties = { reinterpret_cast<char*>(B.ties), uint32_t(sizeof(PathTie)) };
+        I.set_pair_buffer(view_, io, B.pairs, pair_capacity, B.region_count);
+        io.cursor_traverse = B.ctr + 1; io.q_overflow = B.overflow; io.n_overflow = B.ctr + 3;
+        io.t_min = t_min; io.t_max = t_max;
+        io.batch_rays = rays_dev + first * 7;
+        io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
+        io.batch_out = out_dev + first;
+        I.launch_trace<true>(view_, io, I.wb, RoundParams{}, 0, st, nullptr, two_phase);
+        // rays k_finish flagged (pairs did not fit, or more exact ties than the list holds): the one-phase walk
+        k_trace_batch<<<I.sm_count * 8, 128, 0, st>>>(view_, io.batch_rays, B.overflow, 0, B.ctr + 3, B.overflow_total, t_min, t_max,
+                                                      io.batch_xi, io.batch_out);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    CUDA_CHECK(cudaEventRecord(B.e1, st));
+    unsigned long long n_over = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_over, B.overflow_total, sizeof(n_over), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    last_trace_overflow_ = n_over;
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, B.e0, B.e1));
     return ms;
 }
 
@@ -1534,6 +1617,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (I.list_capacity < n_pixels) {
         for (int k = 0; k < 2; ++k) { if (I.list[k]) cudaFree(I.list[k]); I.list[k] = nullptr; }
         if (I.tile_list) { cudaFree(I.tile_list); I.tile_list = nullptr; }
+        I.tile_key[4] = -1;
         if (I.lumsq) { cudaFree(I.lumsq); I.lumsq = nullptr; }
         for (int k = 0; k < 2; ++k) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.list[k]), n_pixels * sizeof(uint32_t)));
         CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.tile_list), n_pixels * sizeof(uint32_t)));
@@ -1548,15 +1632,36 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
         base_list = p.pixel_list_dev;
         n_local = p.n_pixel_list;
     } else if (p.tile_parts > 1) {
-        std::vector<uint32_t> mine;
+        // built on the device and kept: the same (size, tiling, part) comes back on every step of a multi-GPU render
         const int ts = std::max(p.tile_size, 1);
-        const int tiles_x = (p.width + ts - 1) / ts;
-        for (int y = 0; y < p.height; ++y)
-            for (int x = 0; x < p.width; ++x)
-                if (((y / ts) * tiles_x + (x / ts)) % p.tile_parts == p.tile_part) mine.push_back(uint32_t(y * p.width + x));
-        n_local = mine.size();
-        if (n_local) CUDA_CHECK(cudaMemcpyAsync(I.tile_list, mine.data(), n_local * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        const int key[5] = { p.width, p.height, ts, p.tile_parts, p.tile_part };
+        if (std::memcmp(key, I.tile_key, sizeof(key)) != 0) {
+            const int tiles_x = (p.width + ts - 1) / ts, tiles_y = (p.height + ts - 1) / ts;
+            const long long n_tiles = (long long)tiles_x * tiles_y;
+            const long long n_owned = p.tile_part < n_tiles ? (n_tiles - 1 - p.tile_part) / p.tile_parts + 1 : 0;
+            std::vector<uint32_t> offsets(size_t(std::max<long long>(n_owned, 1)));
+            size_t count = 0;               // pixels of the owned tiles (per-tile arithmetic, no per-pixel loop)
+            for (long long k = 0; k < n_owned; ++k) {
+                const long long t = p.tile_part + k * p.tile_parts;
+                const int tx = int(t % tiles_x), ty = int(t / tiles_x);
+                offsets[size_t(k)] = uint32_t(count);
+                count += size_t(std::min(ts, p.width - tx * ts)) * size_t(std::min(ts, p.height - ty * ts));
+            }
+            if (n_owned) {
+                if (I.tile_offsets_capacity < size_t(n_owned)) {
+                    if (I.tile_offsets) { cudaFree(I.tile_offsets); I.tile_offsets = nullptr; I.tile_offsets_capacity = 0; }
+                    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.tile_offsets), size_t(n_owned) * sizeof(uint32_t)));
+                    I.tile_offsets_capacity = size_t(n_owned);
+                }
+                CUDA_CHECK(cudaMemcpyAsync(I.tile_offsets, offsets.data(), size_t(n_owned) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                k_tile_list<<<unsigned(n_owned), 256, 0, st>>>(I.tile_list, I.tile_offsets, p.width, p.height, ts, p.tile_parts, p.tile_part);
+                CUDA_CHECK(cudaGetLastError());
+                CUDA_CHECK(cudaStreamSynchronize(st));      // `offsets` lives on this frame (once per key, not per call)
+            }
+            std::memcpy(I.tile_key, key, sizeof(key));
+            I.tile_count = count;
+        }
+        n_local = I.tile_count;
         base_list = I.tile_list;
     }
 
@@ -1582,8 +1687,12 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     bool use_walk = true;               // big trees: k_walk + k_finish; ARTB_WALK=0 falls back to the chunked k_extend
     if (const char* e = getenv("ARTB_WALK")) use_walk = atoi(e) != 0;
     RenderStats S;
-    cudaEvent_t ev_begin, ev_end;
-    CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end));
+    struct EventPair {            // destroyed on every exit, including the CUDA_CHECK throws below
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } evp;
+    CUDA_CHECK(cudaEventCreate(&evp.a)); CUDA_CHECK(cudaEventCreate(&evp.b));
+    const cudaEvent_t ev_begin = evp.a, ev_end = evp.b;
     // per-wave events around the kernels of the closest-hit stage (roofline denominator), drained whenever the pool
     // fills up: [5k] before k_traverse, [5k+1] after it, [5k+2] after k_pairs, [5k+3] after k_finish, [5k+4] after k_extend
     const size_t kPairs = 1024;
@@ -1633,7 +1742,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     if (pairs_used == kPairs) drain();
                     CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used], st));
                 }
-                if (two_phase) {
+                if (two_phase || use_walk) {
                     TraceIO io{};
                     io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits; io.ties = w.ties;
                     I.set_pair_buffer(view_, io, w.pairs, w.pair_capacity, w.region_count);
@@ -1641,21 +1750,10 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
                     io.t_min = 0.001; io.t_max = INFINITY;
                     io.rays = w.rays; io.aux = w.aux;
-                    I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr);
-                    k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);
-                    S.launches += 5;
-                } else if (use_walk) {
-                    TraceIO io{};
-                    io.n_ptr = &w.c->n_extend[cur]; io.list = w.q_extend[cur]; io.hits = w.hits; io.ties = w.ties;
-                    io.cursor_traverse = &w.c->cursor[0];
-                    io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
-                    io.t_min = 0.001; io.t_max = INFINITY;
-                    io.rays = w.rays; io.aux = w.aux;
-                    k_walk<false><<<I.sm_count * 4, ARTB_WALK_THREADS, 0, st>>>(io, view_, w.c, cur);
-                    if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 1], st)); CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 2], st)); }
-                    k_finish<false><<<I.sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view_, w, rp, cur);
-                    if (profile) CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 3], st));
-                    S.launches += 3;
+                    I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr, two_phase);
+                    // overflow pass: only the pair kernels can flag rays (full regions, more exact ties than the list holds)
+                    if (two_phase) k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);
+                    S.launches += two_phase ? 5 : 3;
                 } else {
                     if (profile) for (int e = 1; e <= 3; ++e) CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + e], st));
                     k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 1);
@@ -1678,6 +1776,10 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (!p.adaptive) {
         run_round((long long)n_local, base_list, uint32_t(p.sample_begin), uint32_t(p.samples_per_pixel));
         S.samples = (unsigned long long)n_local * (unsigned long long)p.samples_per_pixel;
+        if (count_dev && n_local) {
+            k_count_fixed<<<unsigned((n_local + 255) / 256), 256, 0, st>>>(base_list, uint32_t(n_local), uint32_t(p.samples_per_pixel), count_dev);
+            S.launches++;
+        }
     } else {
         // round 0: every local pixel gets min_spp samples; then only the unconverged ones are re-queued
         const uint32_t max_spp = uint32_t(p.samples_per_pixel);
@@ -1718,7 +1820,6 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     CUDA_CHECK(cudaMemcpy(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost));
     S.rays = I.counters_host->rays;
     S.overflow_rays = I.counters_host->overflow_total;
-    cudaEventDestroy(ev_begin); cudaEventDestroy(ev_end);
     if (stats) *stats = S;
 }
 

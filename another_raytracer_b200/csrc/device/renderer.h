@@ -94,6 +94,8 @@ public:
     int device() const { return device_; }
 
 private:
+    void init(uint32_t pool_paths);
+    void release();
     struct Impl;
     Impl* impl_;
     int device_;
@@ -102,6 +104,7 @@ private:
     SceneView view_{};
     uint64_t scene_bytes_ = 0;
     uint64_t last_trace_overflow_ = 0;
+    uint32_t max_dfs_id_ = 0;         // largest depth-first leaf id among the world primitives (shade_batch maps ids back)
     BvhBuildStats last_build_{};
 };
 

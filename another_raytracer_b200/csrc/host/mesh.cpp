@@ -296,6 +296,32 @@ bool mesh::parse(const std::string& mesh_path)
     return true;
 }
 
+std::shared_ptr<material> mesh::face_material(size_t i, std::map<std::string, std::shared_ptr<image_texture>>& material_maps)
+{
+    const std::vector<obj_index>& indices = parse_data.indices;
+    auto texcoord = [this](int index) -> std::pair<double, double> {
+        const std::vector<float>& t = parse_data.texcoords;
+        return { t[size_t(2 * index) + 0], t[size_t(2 * index) + 1] };
+    };
+    if (parse_data.materials.empty()) return std::make_shared<lambertian>(color::random());      // mesh.h:132-138
+    const int mid = parse_data.material_ids[i];
+    if (mid < 0) throw std::logic_error("obj: face without material in a file that declares materials");
+    const obj_material& m = parse_data.materials[size_t(mid)];
+    if (!m.diffuse_texname.empty()) {
+        auto it = material_maps.find(m.diffuse_texname);
+        if (it == material_maps.end())
+            it = material_maps.emplace(m.diffuse_texname,
+                                       std::make_shared<image_texture>(model_work_path + "/" + m.diffuse_texname)).first;
+        auto tex = std::make_shared<barycentric_image_texture>(
+            texcoord(indices[3 * i + 0].texcoord_index),
+            texcoord(indices[3 * i + 1].texcoord_index),
+            texcoord(indices[3 * i + 2].texcoord_index), it->second);
+        return std::make_shared<lambertian>(tex);
+    }
+    // reference: mesh.h:128 — float sums widened to double
+    return std::make_shared<lambertian>(color(m.ambient[0] + m.diffuse[0], m.ambient[1] + m.diffuse[1], m.ambient[2] + m.diffuse[2]));
+}
+
 hittable_list mesh::build()
 {
     hittable_list triangles;
@@ -305,40 +331,27 @@ hittable_list mesh::build()
         const std::vector<float>& p = parse_data.positions;
         return vec3(p[size_t(3 * index) + 0], p[size_t(3 * index) + 1], p[size_t(3 * index) + 2]);
     };
-    auto texcoord = [this](int index) -> std::pair<double, double> {
-        const std::vector<float>& t = parse_data.texcoords;
-        return { t[size_t(2 * index) + 0], t[size_t(2 * index) + 1] };
-    };
 
     const std::vector<obj_index>& indices = parse_data.indices;
     for (size_t i = 0; i < indices.size() / 3; ++i) {
         const vec3 a = vertex(indices[3 * i + 0].position_index);
         const vec3 b = vertex(indices[3 * i + 1].position_index);
         const vec3 c = vertex(indices[3 * i + 2].position_index);
-        if (!parse_data.materials.empty()) {
-            const int mid = parse_data.material_ids[i];
-            if (mid < 0) throw std::logic_error("obj: face without material in a file that declares materials");
-            const obj_material& m = parse_data.materials[size_t(mid)];
-            if (!m.diffuse_texname.empty()) {
-                auto it = material_maps.find(m.diffuse_texname);
-                if (it == material_maps.end())
-                    it = material_maps.emplace(m.diffuse_texname,
-                                               std::make_shared<image_texture>(model_work_path + "/" + m.diffuse_texname)).first;
-                auto tex = std::make_shared<barycentric_image_texture>(
-                    texcoord(indices[3 * i + 0].texcoord_index),
-                    texcoord(indices[3 * i + 1].texcoord_index),
-                    texcoord(indices[3 * i + 2].texcoord_index), it->second);
-                triangles.add(std::make_shared<triangle>(a, b, c, std::make_shared<lambertian>(tex)));
-            } else {
-                // reference: mesh.h:128 — float sums widened to double
-                triangles.add(std::make_shared<triangle>(a, b, c, std::make_shared<lambertian>(
-                    color(m.ambient[0] + m.diffuse[0], m.ambient[1] + m.diffuse[1], m.ambient[2] + m.diffuse[2]))));
-            }
-        } else {
-            triangles.add(std::make_shared<triangle>(a, b, c, std::make_shared<lambertian>(color::random())));
-        }
+        triangles.add(std::make_shared<triangle>(a, b, c, face_material(i, material_maps)));
     }
     return triangles;
+}
+
+// Direct path: the same triangles and the same per-face materials as build(), held as ONE object. Textured faces keep
+// their barycentric_image_texture; the flattener puts every distinct map_Kd image into the device texel atlas once.
+std::shared_ptr<triangle_soup> mesh::build_soup()
+{
+    std::map<std::string, std::shared_ptr<image_texture>> material_maps;
+    auto soup = build_soup(std::shared_ptr<material>());
+    soup->materials.clear();
+    soup->materials.reserve(soup->faces.size());
+    for (size_t i = 0; i < soup->faces.size(); ++i) soup->materials.push_back(face_material(i, material_maps));
+    return soup;
 }
 
 std::shared_ptr<triangle_soup> mesh::build_soup(std::shared_ptr<material> mat) const

@@ -46,12 +46,16 @@ class mesh {
 public:
     bool parse(const std::string& mesh_path);           // reference: mesh.h:31-65
     hittable_list build();                               // reference: mesh.h:67-145 (one triangle object per face)
-    // NEW: whole mesh as a single triangle_soup with one shared material
+    // NEW: whole mesh as a single triangle_soup — with one shared material, or with the per-face
+    // materials build() would give the triangle objects (same colours, same map_Kd image textures, same RNG draws)
     std::shared_ptr<triangle_soup> build_soup(std::shared_ptr<material> mat) const;
+    std::shared_ptr<triangle_soup> build_soup();
     size_t num_triangles() const { return parse_data.indices.size() / 3; }
 
     obj_data parse_data;
 private:
+    // material of face i as mesh.h:104-138 chooses it; `maps` caches the decoded map_Kd images (material_map_handler)
+    std::shared_ptr<material> face_material(size_t i, std::map<std::string, std::shared_ptr<image_texture>>& maps);
     std::string model_work_path;
 };
 

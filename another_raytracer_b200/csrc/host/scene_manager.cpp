@@ -218,17 +218,23 @@ static hittable_list build_next_week_final()
     return objects;
 }
 
-// reference: scene_manager.cpp:236-258
-static hittable_list build_mesh_scene(const std::string& obj_path, bool mesh_as_soup)
+// reference: scene_manager.cpp:236-258. all_metal: BASELINE configs[3]'s metal variant — the mesh is built exactly as the
+// reference builds it (per-triangle lambertians, random colours drawn), then every triangle gets the one metal.
+static hittable_list build_mesh_scene(const std::string& obj_path, bool mesh_as_soup, bool all_metal = false)
 {
     mesh m;
     if (!m.parse(obj_path)) throw std::logic_error("cannot parse input obj file!");
 
+    const auto steel = all_metal ? mk<metal>(color(0.8, 0.8, 0.9), 0.1) : std::shared_ptr<metal>();
     hittable_list world;
     if (mesh_as_soup) {
-        world.add(m.build_soup(mk<lambertian>(color(0.6, 0.6, 0.6))));
+        auto soup = m.build_soup();
+        if (all_metal) soup->materials.assign(1, steel);
+        world.add(soup);
     } else {
         hittable_list triangles = m.build();
+        if (all_metal)
+            for (auto& o : triangles.objects) static_cast<triangle&>(*o).mat_ptr = steel;
         world.add(mk<bvh_node>(triangles, 0.0, 1.0));
     }
     world.add(mk<xz_rect>(123, 423, 147, 412, 554, mk<diffuse_light>(color(7, 7, 7))));
@@ -353,6 +359,20 @@ scene scene_manager::build(scene_alias alias)
             break;
         case scene_alias::dino:
             world.objects = build_mesh_scene(assets_root() + "/models/dino.obj", mesh_as_soup);
+            world.background = sky;
+            world.lookfrom = point3(0, 15, 25);
+            world.lookat = point3(0, 10, 0);
+            world.vfov = 75.0;
+            break;
+        case scene_alias::cow_metal:
+            world.objects = build_mesh_scene(assets_root() + "/models/cow.obj", mesh_as_soup, true);
+            world.background = sky;
+            world.lookfrom = point3(4, 2, 6);
+            world.lookat = point3(2, 0, 0);
+            world.vfov = 75.0;
+            break;
+        case scene_alias::dino_metal:
+            world.objects = build_mesh_scene(assets_root() + "/models/dino.obj", mesh_as_soup, true);
             world.background = sky;
             world.lookfrom = point3(0, 15, 25);
             world.lookat = point3(0, 10, 0);

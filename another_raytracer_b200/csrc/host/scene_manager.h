@@ -8,6 +8,9 @@
 //   cow = 10, dino = 11   the reference's _mesh_scene assembly (scene_manager.cpp:236-258) around
 //                         models/cow.obj / models/dino.obj with the camera presets the reference keeps as
 //                         comments (scene_manager.cpp:337-342)
+//   cow_metal = 13, dino_metal = 14   the same two scenes, every triangle under metal(0.8, 0.8, 0.9; fuzz 0.1): the
+//                         per-triangle lambertians are still created (and draw their random colours) before being
+//                         replaced, so the global RNG advances exactly as in aliases 10 / 11
 //   heightfield = 12      synthetic closed-form 708x708-vertex height field = 999 698 triangles,
 //                         one triangle_soup, a light and a sky background
 #ifndef ARTB_HOST_SCENE_MANAGER_H
@@ -40,7 +43,9 @@ enum class scene_alias {
     mesh = 9,
     cow = 10,
     dino = 11,
-    heightfield = 12
+    heightfield = 12,
+    cow_metal = 13,       // BASELINE.json configs[3] "under Lambertian/metal": the same meshes with every triangle's
+    dino_metal = 14       // material replaced by one metal (unnormalised triangle normals reach metal::scatter)
 };
 
 // asset root: $ARTB_ASSETS or <repo>/assets (set_assets_root overrides both)

@@ -44,7 +44,7 @@ struct hit_record {                       // hittable.h:9-23
 };
 
 struct query_ctx {
-    const std::unordered_map<const hittable*, int>* leaf_ids = nullptr;
+    const std::unordered_map<const hittable*, int>* leaf_ids = nullptr;   // a triangle_soup maps to the id of its first face
     int last_leaf = -1;                   // id of the last world leaf that reported a hit
     int boundary_depth = 0;               // > 0 while a medium queries its boundary
     const double* xi_row = nullptr;       // explicit xi per medium slot (nullptr: draw from the global stream)
@@ -332,8 +332,31 @@ bool hit_any(const hittable& h, const ray& r, double t_min, double t_max, hit_re
             note_leaf(h, q);
             return true;
         }
-        case hittable_kind::triangle_soup:
-            throw std::logic_error("oracle: triangle_soup is not a reference construct");
+        case hittable_kind::triangle_soup: {
+            // Not a reference class: it stands for the hittable_list of `triangle` objects with the same vertices and
+            // materials (that is how graph_dump serialises it), so it is intersected as hittable_list::hit would
+            // (hittable_list.cpp:5-19): every face in order, t_max narrowed to the closest so far, later faces win ties.
+            const auto& sp = static_cast<const triangle_soup&>(h);
+            hit_record temp_rec;
+            bool hit_anything = false;
+            double closest_so_far = t_max;
+            int base = -1;
+            if (q.boundary_depth == 0 && q.leaf_ids) { auto it = q.leaf_ids->find(&h); if (it != q.leaf_ids->end()) base = it->second; }
+            triangle tr(point3(0, 0, 0), point3(0, 0, 0), point3(0, 0, 0), nullptr);
+            for (size_t f = 0; f < sp.faces.size(); ++f) {
+                tr.pt1 = sp.vertices[size_t(sp.faces[f][0])];
+                tr.pt2 = sp.vertices[size_t(sp.faces[f][1])];
+                tr.pt3 = sp.vertices[size_t(sp.faces[f][2])];
+                if (hit_triangle(tr, r, t_min, closest_so_far, temp_rec)) {
+                    hit_anything = true;
+                    closest_so_far = temp_rec.t;
+                    rec = temp_rec;
+                    rec.mat_ptr = sp.materials[sp.materials.size() == 1 ? 0 : f].get();
+                    if (base >= 0) q.last_leaf = base + int(f);
+                }
+            }
+            return hit_anything;
+        }
     }
     return false;
 }
@@ -533,6 +556,10 @@ struct oracle_scene {
                 number(*static_cast<const constant_medium&>(h).boundary, true);
                 break;
             }
+            case hittable_kind::triangle_soup:        // one id per face, in face order (what the flattener hands out)
+                if (!in_boundary) leaf_ids[&h] = n_leaves;
+                n_leaves += int(static_cast<const triangle_soup&>(h).faces.size());
+                break;
             default:
                 if (!in_boundary) leaf_ids[&h] = n_leaves;
                 n_leaves++;
@@ -547,13 +574,16 @@ struct oracle_hit {
     std::int32_t hit, prim_id, front_face, material_type;
 };
 
-ORACLE_API void* oracle_scene_build(int alias, const char* assets_root)
+// mesh_as_soup / heightfield_side: the scene_manager options of include/artb.h's artb_scene_options (0 = default)
+ORACLE_API void* oracle_scene_build_opt(int alias, const char* assets_root, int mesh_as_soup, int heightfield_side)
 {
     try {
         if (assets_root) set_assets_root(assets_root);
         reset_global_rng();
         auto* o = new oracle_scene;
         scene_manager mgr;
+        mgr.mesh_as_soup = mesh_as_soup != 0;
+        if (heightfield_side > 0) mgr.heightfield_side = heightfield_side;
         o->s = mgr.build(static_cast<scene_alias>(alias));
         o->number(o->s.objects, false);
         return o;
@@ -562,6 +592,8 @@ ORACLE_API void* oracle_scene_build(int alias, const char* assets_root)
         return nullptr;
     }
 }
+
+ORACLE_API void* oracle_scene_build(int alias, const char* assets_root) { return oracle_scene_build_opt(alias, assets_root, 0, 0); }
 
 ORACLE_API void oracle_scene_free(void* h) { delete static_cast<oracle_scene*>(h); }
 ORACLE_API int oracle_scene_n_media(void* h) { return static_cast<oracle_scene*>(h)->n_media; }

@@ -24,6 +24,8 @@ def load():
         lib = C.CDLL(str(PORT_LIB))
         lib.oracle_scene_build.argtypes = [C.c_int, C.c_char_p]
         lib.oracle_scene_build.restype = C.c_void_p
+        lib.oracle_scene_build_opt.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int]
+        lib.oracle_scene_build_opt.restype = C.c_void_p
         lib.oracle_scene_free.argtypes = [C.c_void_p]
         lib.oracle_scene_n_media.argtypes = [C.c_void_p]
         lib.oracle_scene_n_leaves.argtypes = [C.c_void_p]
@@ -41,9 +43,9 @@ def load():
 class OracleScene:
     """A scene built by the host mirror and intersected / shaded on the CPU with the reference's algorithm."""
 
-    def __init__(self, alias: int):
+    def __init__(self, alias: int, mesh_as_soup: bool = False, heightfield_side: int = 0):
         self.lib = load()
-        self.h = self.lib.oracle_scene_build(int(alias), str(ROOT / "assets").encode())
+        self.h = self.lib.oracle_scene_build_opt(int(alias), str(ROOT / "assets").encode(), int(mesh_as_soup), int(heightfield_side))
         if not self.h:
             raise RuntimeError("oracle scene build failed")
         self.n_media = self.lib.oracle_scene_n_media(self.h)

@@ -42,7 +42,8 @@ def psnr8(a, b):
 # alias, W, H, oracle spp per image, GPU spp
 FLOOR_CASES = [(1, 120, 68, 16, 4096), (6, 96, 96, 32, 8192), (7, 64, 64, 32, 8192), (8, 96, 96, 16, 8192),
                (3, 80, 45, 16, 2048), (4, 80, 45, 16, 2048), (5, 80, 45, 64, 8192), (9, 96, 54, 8, 2048),
-               (10, 96, 54, 8, 2048), (11, 96, 54, 8, 2048), (2, 80, 45, 16, 2048)]
+               (10, 96, 54, 8, 2048), (11, 96, 54, 8, 2048), (2, 80, 45, 16, 2048),
+               (13, 96, 54, 8, 2048), (14, 96, 54, 8, 2048)]
 
 
 @pytest.mark.parametrize("alias,w,h,m,n", FLOOR_CASES, ids=[f"scene{c[0]}" for c in FLOOR_CASES])

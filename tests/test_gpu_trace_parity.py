@@ -14,7 +14,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-5          # north_star tolerance for t and the normal
-ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
+ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14]
 MAT_CODE = {200: 0, 201: 1, 202: 2, 203: 3, 204: 4}
 
 

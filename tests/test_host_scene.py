@@ -34,7 +34,7 @@ def test_rng_matches_libstdcxx_over_a_long_run(artb):
     assert np.array_equal(got, np.minimum(expect, np.nextafter(1.0, 0.0)))
 
 
-@pytest.mark.parametrize("alias", range(1, 12))
+@pytest.mark.parametrize("alias", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14])
 def test_scene_graph_identical_to_reference(artb, alias):
     """Same objects, same order, same doubles, same BVH shapes, same Perlin tables and texels as the reference, and
     the global RNG left at the same position."""

@@ -9,7 +9,7 @@ import another_raytracer_b200 as A
 import hostsim_lib as H
 from conftest import GOLDEN
 
-ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]
+ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14]
 
 
 @pytest.mark.parametrize("alias", ALIASES)

@@ -21,7 +21,7 @@ def test_single_mode_render_is_bit_identical(path):
     assert np.array_equal(lin, g["lin"])
 
 
-@pytest.mark.parametrize("alias", range(1, 12))
+@pytest.mark.parametrize("alias", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14])
 def test_recorded_queries_are_reproduced_exactly(alias):
     """every closest-hit query the reference made: same winning leaf id, bit-identical t / p / normal / front_face"""
     g = np.load(GOLDEN / f"trace_{alias}.npz")

@@ -28,9 +28,11 @@ TRACE = {   # alias: (W, H, stride, spp, max_rays)
     1: (400, 225, 9, 1, 3000), 2: (200, 112, 12, 1, 600), 3: (200, 112, 12, 1, 600), 4: (200, 112, 12, 1, 600),
     5: (200, 112, 8, 1, 1200), 6: (300, 300, 10, 1, 4000), 7: (300, 300, 12, 1, 3000), 8: (400, 400, 11, 1, 5000),
     9: (320, 180, 9, 1, 2500), 10: (320, 180, 9, 1, 2500), 11: (320, 180, 9, 1, 2500),
+    13: (320, 180, 9, 1, 2500), 14: (320, 180, 9, 1, 2500),        # cow / dino under metal (BASELINE configs[3])
 }
 IMAGES = [(1, 120, 68, 4), (6, 96, 96, 8), (7, 64, 64, 8), (8, 96, 96, 4), (9, 96, 54, 2), (10, 96, 54, 2), (11, 96, 54, 2),
-          (3, 80, 45, 4), (4, 80, 45, 4), (5, 80, 45, 8), (2, 80, 45, 4)]
+          (3, 80, 45, 4), (4, 80, 45, 4), (5, 80, 45, 8), (2, 80, 45, 4), (13, 96, 54, 2), (14, 96, 54, 2)]
+ALIASES = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 14]     # 12 (height field) is not a reference scene: the oracle port covers it
 
 
 def run(*args):
@@ -71,28 +73,42 @@ def read_trace(path):
 
 
 def main():
+    """usage: make_golden.py [--info-only] [--only ALIAS ...]   (--only: refresh just these aliases, keep the other files)"""
     if not TOOL.exists():
         sys.exit("oracle/_ref/ref_tool missing: run `make -C oracle` where /root/reference exists")
+    only = None
+    if "--only" in sys.argv:
+        only = {int(a) for a in sys.argv[sys.argv.index("--only") + 1:] if a.isdigit()}
     OUT.mkdir(parents=True, exist_ok=True)
-    info = {"rng_first": [float(x) for x in run("rng", 8).split()],
-            "sphere_uv": [[float(x) for x in l.split()] for l in run("uv").splitlines() if l.strip()], "scenes": {}}
+    info_path = OUT / "scene_info.json"
+    if only and info_path.exists():
+        info = json.loads(info_path.read_text())
+    else:
+        info = {"rng_first": [float(x) for x in run("rng", 8).split()],
+                "sphere_uv": [[float(x) for x in l.split()] for l in run("uv").splitlines() if l.strip()], "scenes": {}}
     import hashlib
     with tempfile.TemporaryDirectory() as tmp:
-        for alias in range(1, 12):
+        for alias in ALIASES:
+            if only and alias not in only:
+                continue
             info["scenes"][str(alias)] = last_json(run("info", alias))
             p = os.path.join(tmp, "g.bin")
             run("graph", alias, p)
             info["scenes"][str(alias)]["stream_sha256"] = hashlib.sha256(open(p, "rb").read()).hexdigest()
-    (OUT / "scene_info.json").write_text(json.dumps(info, indent=1))
+    info_path.write_text(json.dumps(info, indent=1))
     if "--info-only" in sys.argv:
         return
     with tempfile.TemporaryDirectory() as tmp:
         for alias, (w, h, stride, spp, max_rays) in TRACE.items():
+            if only and alias not in only:
+                continue
             p = os.path.join(tmp, "t.bin")
             print("trace", alias, last_json(run("trace", alias, w, h, stride, spp, max_rays, p)))
             d = read_trace(p)
             np.savez_compressed(OUT / f"trace_{alias}.npz", **d)
         for alias, w, h, spp in IMAGES:
+            if only and alias not in only:
+                continue
             p = os.path.join(tmp, "i.raw")
             print("render", alias, last_json(run("render", alias, w, h, spp, p)))
             rgb = np.fromfile(p, dtype=np.uint8).reshape(h, w, 3)
