@@ -2,7 +2,7 @@
 blackccpie/another_raytracer, behind the C ABI in include/artb.h. See DESIGN.md."""
 from ._abi import LIB_PATH, SYMBOLS, load  # noqa: F401
 from .engine import (ArtbError, CameraDesc, Context, Engine, EngineMode, HIT_DTYPE, MATERIAL_NAMES, RenderOptions,  # noqa: F401
-                     Scene, SceneAlias)
+                     SHADE_DTYPE, Scene, SceneAlias)
 
 __all__ = ["ArtbError", "CameraDesc", "Context", "Engine", "EngineMode", "HIT_DTYPE", "MATERIAL_NAMES", "RenderOptions",
-           "Scene", "SceneAlias", "LIB_PATH", "SYMBOLS", "load"]
+           "SHADE_DTYPE", "Scene", "SceneAlias", "LIB_PATH", "SYMBOLS", "load"]

@@ -16,9 +16,10 @@ LIB_PATH = _PKG / "libartb.so"
 # every symbol include/artb.h declares (tests/test_abi_symbols.py checks the header against this list)
 SYMBOLS = [
     "artb_abi_version", "artb_create", "artb_destroy", "artb_last_error",
-    "artb_scene_build", "artb_scene_free", "artb_scene_get_info", "artb_scene_dump_graph", "artb_scene_get_flat",
+    "artb_scene_build", "artb_scene_from_graph", "artb_scene_free", "artb_scene_get_info", "artb_scene_dump_graph", "artb_scene_get_flat",
     "artb_upload_scene", "artb_upload_flat",
     "artb_trace_batch", "artb_trace_batch_device", "artb_trace_overflow_rays",
+    "artb_shade_batch", "artb_camera_rays",
     "artb_build_bvh_device", "artb_last_bvh_build",
     "artb_render", "artb_render_device", "artb_resolve_device", "artb_stream",
     "artb_save_png", "artb_host_rng_reset", "artb_host_rng_next",
@@ -36,6 +37,10 @@ class Config(C.Structure):
 class SceneOptions(C.Structure):
     _fields_ = [("mesh_as_soup", C.c_int32), ("heightfield_side", C.c_int32), ("max_leaf_prims", C.c_int32),
                 ("device_bvh", C.c_int32), ("assets_root", C.c_char_p)]
+
+
+class GraphBlob(C.Structure):
+    _fields_ = [("hash", C.c_uint64), ("data", C.c_void_p), ("bytes", C.c_uint64)]
 
 
 class SceneInfo(C.Structure):
@@ -66,6 +71,12 @@ class FlatSceneView(C.Structure):
 class Hit(C.Structure):
     _fields_ = [("t", C.c_double), ("p", C.c_double * 3), ("normal", C.c_double * 3), ("u", C.c_double), ("v", C.c_double),
                 ("hit", C.c_int32), ("prim_id", C.c_int32), ("front_face", C.c_int32), ("material_type", C.c_int32)]
+
+
+class ShadeRecord(C.Structure):
+    _fields_ = [("emitted", C.c_double * 3), ("attenuation", C.c_double * 3), ("origin", C.c_double * 3),
+                ("direction", C.c_double * 3), ("time", C.c_double), ("scattered", C.c_int32), ("material_type", C.c_int32),
+                ("front_face", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Camera(C.Structure):
@@ -116,6 +127,9 @@ def load() -> C.CDLL:
     lib.artb_last_error.argtypes = [vp]
     lib.artb_last_error.restype = C.c_char_p
     lib.artb_scene_build.argtypes = [C.c_int32, C.POINTER(SceneOptions), C.POINTER(vp)]
+    lib.artb_scene_from_graph.argtypes = [vp, C.c_int64, C.POINTER(GraphBlob), C.c_int32, C.POINTER(C.c_double * 3),
+                                          C.POINTER(SceneOptions), C.POINTER(vp)]
+    lib.artb_scene_from_graph.restype = C.c_int
     lib.artb_scene_free.argtypes = [vp]
     lib.artb_scene_free.restype = None
     lib.artb_scene_get_info.argtypes = [vp, C.POINTER(SceneInfo)]
@@ -126,6 +140,10 @@ def load() -> C.CDLL:
     lib.artb_upload_flat.argtypes = [vp, C.POINTER(FlatSceneView)]
     lib.artb_trace_batch.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp]
     lib.artb_trace_batch_device.argtypes = [vp, vp, C.c_uint64, C.c_double, C.c_double, vp, vp, C.POINTER(C.c_float)]
+    lib.artb_shade_batch.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp]
+    lib.artb_shade_batch.restype = C.c_int
+    lib.artb_camera_rays.argtypes = [vp, C.POINTER(Camera), vp, vp, C.c_uint64, vp]
+    lib.artb_camera_rays.restype = C.c_int
     lib.artb_build_bvh_device.argtypes = [vp, C.c_int32, C.POINTER(BvhStats)]
     lib.artb_build_bvh_device.restype = C.c_int
     lib.artb_last_bvh_build.argtypes = [vp, C.POINTER(BvhStats)]

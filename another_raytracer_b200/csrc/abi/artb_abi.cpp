@@ -9,7 +9,9 @@
 #include "../host/scene_manager.h"
 
 #include <cmath>
+#include <climits>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -31,6 +33,7 @@ struct artb_ctx {
 };
 
 static_assert(sizeof(artb_hit) == sizeof(HitRecordOut), "artb_hit must match the device record");
+static_assert(sizeof(artb_shade_record) == sizeof(ShadeRecordOut), "artb_shade_record must match the device record");
 static_assert(sizeof(FlatPrim) == 96 && sizeof(FlatNode8) == 80 && sizeof(FlatXformOp) == 32 && sizeof(FlatXform) == 8 &&
               sizeof(FlatMaterial) == 48 && sizeof(FlatTexture) == 96 && sizeof(FlatImage) == 24 && sizeof(FlatPerlin) == 9216,
               "flat record sizes are part of the ABI");
@@ -85,6 +88,8 @@ int check_render_args(artb_ctx* ctx, const artb_camera* cam, const artb_render_p
         return fail(ctx, ARTB_E_EMPTY_SCENE, "Invalid input scene!");
     }
     if (p->width < 2 || p->height < 2) return fail(ctx, ARTB_E_INVALID, "image must be at least 2x2");
+    // pixel and component indices are 32-bit on the device (PathAux::pixel, the resolve kernels)
+    if (uint64_t(p->width) * uint64_t(p->height) * 3u > uint64_t(INT_MAX)) return fail(ctx, ARTB_E_INVALID, "image too large: width*height*3 must fit in 31 bits");
     if (p->samples_per_pixel < 1) return fail(ctx, ARTB_E_INVALID, "samples_per_pixel must be >= 1");
     if (p->max_depth < 0) return fail(ctx, ARTB_E_INVALID, "max_depth must be >= 0");
     if (p->tile_parts > 1 && (p->tile_part < 0 || p->tile_part >= p->tile_parts)) return fail(ctx, ARTB_E_INVALID, "tile_part out of range");
@@ -164,6 +169,27 @@ int artb_scene_build(int32_t alias, const artb_scene_options* opt, artb_scene** 
         s->host = mgr.build(static_cast<scene_alias>(alias));
         s->rng_draws = global_rng().draws();
         s->rng_next = random_double();
+        FlattenOptions fo;
+        if (opt && opt->max_leaf_prims > 0) fo.max_leaf_prims = opt->max_leaf_prims;
+        if (opt && opt->device_bvh) fo.device_bvh = true;
+        s->flat = flatten(s->host.objects, s->host.background, fo);
+        *out = s.release();
+        return ARTB_OK;
+    });
+}
+
+int artb_scene_from_graph(const double* tokens, int64_t n_tokens, const artb_graph_blob* blobs, int32_t n_blobs,
+                          const double background[3], const artb_scene_options* opt, artb_scene** out)
+{
+    if (!out) return fail(nullptr, ARTB_E_INVALID, "null argument");
+    *out = nullptr;
+    if (!tokens || n_tokens <= 0 || !background || n_blobs < 0 || (n_blobs && !blobs)) return fail(nullptr, ARTB_E_INVALID, "null argument");
+    static_assert(sizeof(artb_graph_blob) == sizeof(GraphBlob), "blob tables are passed through as they are");
+    return guarded(nullptr, [&]() -> int {
+        auto s = std::make_unique<artb_scene>();
+        s->host.objects = build_graph(tokens, size_t(n_tokens), reinterpret_cast<const GraphBlob*>(blobs), size_t(n_blobs));
+        s->host.background = color(background[0], background[1], background[2]);
+        s->host.lookfrom = point3(0, 0, 0); s->host.lookat = point3(0, 0, 0); s->host.vfov = 0; s->host.aperture = 0;
         FlattenOptions fo;
         if (opt && opt->max_leaf_prims > 0) fo.max_leaf_prims = opt->max_leaf_prims;
         if (opt && opt->device_bvh) fo.device_bvh = true;
@@ -280,8 +306,18 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
         for (const FlatPrim& p : fs.prims) {
             if (p.material >= fs.materials.size() || p.xform >= std::max<size_t>(fs.xforms.size(), 1) || p.type > PRIM_MEDIUM)
                 throw std::logic_error("flat scene: primitive refers to a missing material / transform");
-            if (p.type == PRIM_MEDIUM && (p.g[1] < fs.n_world_prims || p.g[1] + p.g[2] > double(fs.prims.size())))
-                throw std::logic_error("flat scene: medium boundary range out of bounds");
+            if (p.type == PRIM_MEDIUM) {
+                // first boundary primitive, boundary count, medium slot: stored as doubles, used as integers on the device — a
+                // NaN, a negative or a fractional value would turn into an arbitrary index there
+                auto whole = [](double v) { return std::isfinite(v) && v >= 0 && v <= 4294967295.0 && v == std::floor(v); };
+                if (!whole(p.g[1]) || !whole(p.g[2]) || !whole(p.g[3]))
+                    throw std::logic_error("flat scene: medium boundary range / slot must be non-negative integers");
+                if (p.g[1] < fs.n_world_prims || p.g[2] < 1 || p.g[1] + p.g[2] > double(fs.prims.size()))
+                    throw std::logic_error("flat scene: medium boundary range out of bounds");
+                if (p.g[3] >= double(fs.n_media)) throw std::logic_error("flat scene: medium slot >= n_media");
+                for (uint32_t b = uint32_t(p.g[1]); b < uint32_t(p.g[1] + p.g[2]); ++b)
+                    if (fs.prims[b].type == PRIM_MEDIUM) throw std::logic_error("flat scene: a medium inside a medium boundary");
+            }
         }
         for (size_t i = 0; i < fs.ref_nodes.size(); ++i) {
             const FlatRefNode& rn = fs.ref_nodes[i];
@@ -293,8 +329,10 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
             if (fs.prims[i].type != PRIM_MEDIUM && !(fs.prims[i].g[9] >= 0 && fs.prims[i].g[9] <= double(fs.ref_nodes.size())))
                 throw std::logic_error("flat scene: primitive refers to a missing reference bvh node (g[9])");
         // BVH primitives without nodes: allowed — Renderer::upload then builds the tree on the device (bvh_build.cuh)
-        if (fs.bvh_depth < 0 || fs.bvh_depth > 24) throw std::logic_error("flat scene: bvh_depth out of range");
-        for (const FlatNode8& n : fs.nodes) {
+        if (fs.bvh_depth < 0 || fs.bvh_depth > ARTB_MAX_BVH8_DEPTH) throw std::logic_error("flat scene: bvh_depth out of range");
+        if (fs.n_media > 255) throw std::logic_error("flat scene: more than 255 media");      // MediumXi keys (bounce << 8) | slot
+        for (size_t ni = 0; ni < fs.nodes.size(); ++ni) {
+            const FlatNode8& n = fs.nodes[ni];
             uint32_t inner = 0;
             for (int sl = 0; sl < 8; ++sl) {
                 const uint32_t m = n.meta[sl];
@@ -313,12 +351,49 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
                     if (n.e[a] < 1 || n.e[a] > 254) throw std::logic_error("flat scene: bad quantisation exponent");
             }
             if (inner && size_t(n.child_base) + inner > fs.nodes.size()) throw std::logic_error("flat scene: BVH child out of bounds");
+            // children strictly after their parent: the node array is a tree laid out forwards, no walk can cycle
+            if (inner && size_t(n.child_base) <= ni) throw std::logic_error("flat scene: BVH child_base must be greater than the node's own index");
         }
         for (const FlatXform& x : fs.xforms)
             if (size_t(x.first_op) + x.n_ops > fs.xform_ops.size() || x.n_ops > 8) throw std::logic_error("flat scene: bad transform chain");
         for (const FlatMaterial& m : fs.materials)
             if (m.type >= MAT_COUNT || ((m.type == MAT_LAMBERTIAN || m.type == MAT_DIFFUSE_LIGHT || m.type == MAT_ISOTROPIC) && m.texture >= fs.textures.size()))
                 throw std::logic_error("flat scene: bad material");
+        for (const FlatImage& im : fs.images) {
+            if (im.width == 0) continue;                                 // "no data": rendered cyan, texels never read
+            if (im.width < 0 || im.height <= 0 || im.bytes_per_pixel < 3 || im.bytes_per_pixel > 4)
+                throw std::logic_error("flat scene: bad image dimensions");
+            const uint64_t bytes = uint64_t(im.width) * uint64_t(im.height) * uint64_t(im.bytes_per_pixel);
+            if (im.offset > fs.texels.size() || bytes > fs.texels.size() - im.offset)
+                throw std::logic_error("flat scene: image extends past the texel atlas");
+        }
+        for (const FlatTexture& t : fs.textures) {
+            if (t.type > TEX_BARY) throw std::logic_error("flat scene: bad texture type");
+            if (t.type == TEX_CHECKER && (t.a >= fs.textures.size() || t.b >= fs.textures.size()))
+                throw std::logic_error("flat scene: checker texture refers to a missing texture");
+            if (t.type == TEX_NOISE && t.a >= fs.perlins.size()) throw std::logic_error("flat scene: noise texture refers to a missing Perlin table");
+            if ((t.type == TEX_IMAGE || t.type == TEX_BARY_IMAGE) && t.a >= fs.images.size())
+                throw std::logic_error("flat scene: image texture refers to a missing image");
+        }
+        {   // checker textures nest (texture.h:31-50): the nesting must be a DAG of depth <= 16 (texture_value's loop bound)
+            std::vector<int> depth(fs.textures.size(), -1);          // -1 unknown, -2 on the current path
+            std::function<int(uint32_t)> walk = [&](uint32_t i) -> int {
+                if (depth[i] == -2) throw std::logic_error("flat scene: checker textures form a cycle");
+                if (depth[i] >= 0) return depth[i];
+                int d = 1;
+                if (fs.textures[i].type == TEX_CHECKER) {
+                    depth[i] = -2;
+                    d = 1 + std::max(walk(fs.textures[i].a), walk(fs.textures[i].b));
+                }
+                if (d > 16) throw std::logic_error("flat scene: checker textures nested deeper than 16");
+                return depth[i] = d;
+            };
+            for (uint32_t i = 0; i < fs.textures.size(); ++i) walk(i);
+        }
+        for (const FlatPerlin& pn : fs.perlins)
+            for (int i = 0; i < 256; ++i)
+                if (uint32_t(pn.perm_x[i]) > 255u || uint32_t(pn.perm_y[i]) > 255u || uint32_t(pn.perm_z[i]) > 255u)
+                    throw std::logic_error("flat scene: Perlin permutation entry out of range");
         ctx->renderer->upload(fs);
         ctx->last_upload_bytes = ctx->renderer->scene_bytes();
         return ARTB_OK;
@@ -345,6 +420,26 @@ int artb_trace_batch_device(artb_ctx* ctx, const double* rays_dev, uint64_t n, d
         const float ms = ctx->renderer->trace_batch_device(rays_dev, n, t_min, t_max, medium_xi_dev,
                                                            reinterpret_cast<HitRecordOut*>(hits_dev));
         if (kernel_ms) *kernel_ms = ms;
+        return ARTB_OK;
+    });
+}
+
+int artb_shade_batch(artb_ctx* ctx, const double* rays, const int32_t* prim_id, const double* t, const double* xi,
+                     uint64_t n, artb_shade_record* out)
+{
+    if (!ctx || (n && (!rays || !prim_id || !t || !xi || !out))) return fail(ctx, ARTB_E_INVALID, "null argument");
+    if (!ctx->renderer->has_scene()) return fail(ctx, ARTB_E_EMPTY_SCENE, "Invalid input scene!");
+    return guarded(ctx, [&]() -> int {
+        ctx->renderer->shade_batch(rays, prim_id, t, xi, n, reinterpret_cast<ShadeRecordOut*>(out));
+        return ARTB_OK;
+    });
+}
+
+int artb_camera_rays(artb_ctx* ctx, const artb_camera* cam, const double* st, const double* xi, uint64_t n, double* rays_out)
+{
+    if (!ctx || !cam || (n && (!st || !xi || !rays_out))) return fail(ctx, ARTB_E_INVALID, "null argument");
+    return guarded(ctx, [&]() -> int {
+        ctx->renderer->camera_rays(make_camera(*cam), st, xi, n, rays_out);
         return ARTB_OK;
     });
 }

@@ -1,5 +1,7 @@
 // flat_scene.h — the flattened scene as it lives in HBM. Plain-old-data shared by the host flattener
-// (g++) and the sm_100a kernels (nvcc). See DESIGN.md "Data layout in HBM".
+// (g++) and the sm_100a kernels (nvcc). See DESIGN.md "Data layout in HBM". The record types themselves are PUBLIC:
+// include/artb_flat.h defines them (a foreign host fills them and calls artb_upload_flat); this header gives them the
+// names the library's own code uses and adds the device-side views.
 //
 // The reference's pointer graph (hittable_list / bvh_node / translate / rotate_y / box / primitives /
 // constant_medium, shared_ptr<material>, shared_ptr<texture>) becomes:
@@ -18,6 +20,8 @@
 
 #include <stdint.h>
 
+#include "artb_flat.h"       // include/: the record definitions are public (a foreign host fills them, artb_upload_flat)
+
 #if defined(__CUDACC__)
 #define ARTB_ALIGN(n) __align__(n)
 #else
@@ -26,100 +30,27 @@
 
 namespace artb {
 
+// the public records under the names the library's C++ / CUDA code uses
+using FlatPrim = ::artb_flat_prim;
+using FlatNode8 = ::artb_flat_node8;
+using FlatRefNode = ::artb_flat_ref_node;
+using FlatXformOp = ::artb_flat_xform_op;
+using FlatXform = ::artb_flat_xform;
+using FlatMaterial = ::artb_flat_material;
+using FlatTexture = ::artb_flat_texture;
+using FlatImage = ::artb_flat_image;
+using FlatPerlin = ::artb_flat_perlin;
+
 enum : uint32_t {
-    PRIM_SPHERE = 0,    // g = cx cy cz r                      sphere.h:39-65
-    PRIM_MSPHERE = 1,   // g = c0(3) c1(3) t0 t1 r             moving_sphere.h:29-58
-    PRIM_RECT_XY = 2,   // g = x0 x1 y0 y1 k                   aarect.cpp:3-19
-    PRIM_RECT_XZ = 3,   // g = x0 x1 z0 z1 k                   aarect.cpp:21-37
-    PRIM_RECT_YZ = 4,   // g = y0 y1 z0 z1 k                   aarect.cpp:39-55
-    PRIM_TRIANGLE = 5,  // g = p1(3) p2(3) p3(3)               triangle.h:22-88
-    PRIM_MEDIUM = 6     // g = neg_inv_density, first boundary prim, boundary prim count, medium slot
-                        //                                      constant_medium.h:37-82
+    PRIM_SPHERE = ARTB_PRIM_SPHERE, PRIM_MSPHERE = ARTB_PRIM_MSPHERE, PRIM_RECT_XY = ARTB_PRIM_RECT_XY,
+    PRIM_RECT_XZ = ARTB_PRIM_RECT_XZ, PRIM_RECT_YZ = ARTB_PRIM_RECT_YZ, PRIM_TRIANGLE = ARTB_PRIM_TRIANGLE,
+    PRIM_MEDIUM = ARTB_PRIM_MEDIUM
 };
-
-struct ARTB_ALIGN(16) FlatPrim {      // 96 B
-    double g[10];         // every type but PRIM_MEDIUM: g[9] = 1 + index of the innermost reference bvh_node that encloses
-                          // the primitive (FlatRefNode, below), 0 = none
-    uint32_t type;
-    uint32_t material;
-    uint32_t xform;       // 0 = identity
-    uint32_t dfs_id;      // position in the reference's depth-first test order: reported id + tie-break
-};
-
-// 8-wide BVH node with boxes quantised to 8 bits per plane on a per-node grid (the compressed wide BVH of Ylitie,
-// Karras & Laine, HPG 2017): 80 bytes = five 16-byte loads decide up to eight descents, and the whole tree of the
-// reference's scenes (a few hundred nodes) fits in one SM's shared memory, where k_extend stages it.
-//   child box plane (axis a)  =  p[a] + q * 2^(e[a]-127),  q in 0..255; lo planes rounded DOWN, hi planes UP, so the
-//   quantised box CONTAINS the double-precision world box. The node test only has to be conservative (it may admit
-//   a ray that misses, never reject one that hits): every candidate primitive is re-tested with the reference's
-//   double-precision formula, so results do not depend on the tree at all — only the amount of work does.
-//   slot s (0..7): meta[s] = 0                          empty
-//                  meta[s] = 0b001'00000 | (24 + s)     internal child; its node index is child_base + (number of
-//                                                       internal slots below s), imask has bit s set
-//                  meta[s] = unary(count) << 5 | offset  leaf of `count` (1..3) primitives prims[prim_base + offset ..]
-//   Children are placed in slots so that a ray of octant o (bit 2: dx<0, bit 1: dy<0, bit 0: dz<0) meets them roughly
-//   front to back when it visits slots in the order of decreasing (slot XOR (7-o)).
-struct ARTB_ALIGN(16) FlatNode8 {     // 80 B
-    float p[3];
-    uint8_t e[3];
-    uint8_t imask;
-    uint32_t child_base;
-    uint32_t prim_base;
-    uint8_t meta[8];
-    uint8_t qlo[3][8];
-    uint8_t qhi[3][8];
-};
-#define ARTB_MAX_LEAF_PRIMS 3
-
-// One bvh_node of the REFERENCE's own trees (bvh.h:22-25), kept only to break exact ties the way the reference does:
-// bvh_node::hit tests its box with the current closest t as t_max, and aabb::hit rejects t_max <= t_min (aabb.h:25,
-// strict), so a later leaf whose enclosing boxes are entered exactly AT the closest t so far is never visited and
-// cannot overwrite an equal-t hit (rt_intersect.cuh: tie_later_wins). Coincident faces of adjacent boxes do this.
-struct ARTB_ALIGN(16) FlatRefNode {   // 64 B
-    double lo[3], hi[3];  // bvh_node::box, in the space of its transform chain
-    int32_t parent;       // enclosing reference bvh_node (through lists and wrappers), -1 = none
-    uint32_t xform;       // transform chain in force at the node
-    int32_t depth;        // number of enclosing reference bvh_nodes
-    uint32_t pad;
-};
-
-enum : uint32_t { XFORM_TRANSLATE = 0, XFORM_ROTATE_Y = 1 };
-
-struct ARTB_ALIGN(16) FlatXformOp {   // 32 B
-    double a, b, c;       // translate: offset xyz          hittable.cpp:3-12
-                          // rotate_y:  sin_theta, cos_theta hittable.cpp:57-85
-    uint32_t type;
-    uint32_t pad;
-};
-
-struct FlatXform { uint32_t first_op, n_ops; };   // ops are applied first_op .. first_op+n_ops-1 going IN
-
-enum : uint32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4,
-                  MAT_COUNT = 5 };
-
-struct ARTB_ALIGN(16) FlatMaterial {  // 48 B
-    double albedo[3];     // metal only
-    double param;         // metal: fuzz; dielectric: ir
-    uint32_t type;
-    uint32_t texture;     // lambertian / diffuse_light / isotropic
-    uint32_t pad[2];
-};
-
-enum : uint32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3, TEX_BARY_IMAGE = 4, TEX_BARY = 5 };
-
-struct ARTB_ALIGN(16) FlatTexture {   // 96 B
-    double p[9];          // solid: rgb | noise: scale | bary_image: ua va ub vb uc vc | bary: a(3) b(3) c(3)
-    uint32_t type;
-    uint32_t a, b;        // checker: even, odd texture | noise: perlin index | image / bary_image: image index
-    uint32_t pad[3];
-};
-
-struct FlatImage { uint64_t offset; int32_t width, height, bytes_per_pixel, pad; };   // width==0: "no data" => cyan
-
-struct FlatPerlin {       // perlin.h:56-61
-    double ranvec[256][3];
-    int32_t perm_x[256], perm_y[256], perm_z[256];
-};
+enum : uint32_t { XFORM_TRANSLATE = ARTB_XFORM_TRANSLATE, XFORM_ROTATE_Y = ARTB_XFORM_ROTATE_Y };
+enum : uint32_t { MAT_LAMBERTIAN = ARTB_MAT_LAMBERTIAN, MAT_METAL = ARTB_MAT_METAL, MAT_DIELECTRIC = ARTB_MAT_DIELECTRIC,
+                  MAT_DIFFUSE_LIGHT = ARTB_MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = ARTB_MAT_ISOTROPIC, MAT_COUNT = ARTB_MAT_COUNT };
+enum : uint32_t { TEX_SOLID = ARTB_TEX_SOLID, TEX_CHECKER = ARTB_TEX_CHECKER, TEX_NOISE = ARTB_TEX_NOISE, TEX_IMAGE = ARTB_TEX_IMAGE,
+                  TEX_BARY_IMAGE = ARTB_TEX_BARY_IMAGE, TEX_BARY = ARTB_TEX_BARY };
 
 // device-side view (all pointers are device pointers)
 // Code path a primitive takes in the double-precision test: k_pairs sorts each tile of pairs by it so that the lanes of
@@ -163,6 +94,14 @@ struct CameraParams {     // camera.h:49-56 + engine.h:62-63
 struct ARTB_ALIGN(8) HitRecordOut {
     double t, p[3], normal[3], u, v;
     int32_t hit, prim_id, front_face, material_type;
+};
+
+// what artb_shade_batch reports per (ray, hit): material::emitted + material::scatter of the hit (material.h:10-135)
+struct ARTB_ALIGN(8) ShadeRecordOut {
+    double emitted[3], attenuation[3];
+    double origin[3], direction[3], time;     // the scattered ray (valid when scattered == 1)
+    int32_t scattered;                        // scatter()'s return value; -1: the hit id does not name a primitive
+    int32_t material_type, front_face, pad;
 };
 
 } // namespace artb

@@ -1142,6 +1142,62 @@ __global__ void __launch_bounds__(128) k_trace_batch(SceneView s, const double* 
     }
 }
 
+// ---- shade-stage parity hooks (artb_shade_batch / artb_camera_rays): the device functions k_shade runs — make_hit_info,
+// material_emitted, material_scatter, texture_value, camera_ray — on explicit inputs with explicit random numbers
+__global__ void k_dfs_map(const FlatPrim* prims, uint32_t n_world, int32_t* map, uint32_t map_size)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_world && prims[i].dfs_id < map_size) map[prims[i].dfs_id] = int32_t(i);
+}
+
+__global__ void __launch_bounds__(128) k_shade_batch(SceneView s, const double* rays, const int32_t* prim_id, const double* t,
+                                                     const double* xi, const int32_t* dfs_map, uint32_t map_size, uint64_t n,
+                                                     ShadeRecordOut* out)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ShadeRecordOut o;
+    memset(&o, 0, sizeof(o));
+    const int32_t id = prim_id[i];
+    const int32_t prim = id >= 0 && uint32_t(id) < map_size ? dfs_map[id] : -1;
+    if (prim < 0) {
+        o.scattered = -1; o.material_type = -1;
+        out[i] = o;
+        return;
+    }
+    DRay r;
+    r.o = ld3(rays + i * 7); r.d = ld3(rays + i * 7 + 3); r.tm = rays[i * 7 + 6];
+    const HitInfo h = make_hit_info(s, prim, r, t[i]);
+    const FlatMaterial& mat = s.materials[h.material];
+    const d3 e = material_emitted(s, mat, h);
+    XiTable g{ xi + i * 4 };
+    d3 att = mk3(0, 0, 0);
+    DRay sc;
+    sc.o = mk3(0, 0, 0); sc.d = mk3(0, 0, 0); sc.tm = 0;
+    const bool ok = material_scatter(s, mat, r, h, g, att, sc);
+    o.emitted[0] = e.x; o.emitted[1] = e.y; o.emitted[2] = e.z;
+    o.scattered = ok ? 1 : 0;
+    o.material_type = int32_t(mat.type);
+    o.front_face = h.front_face ? 1 : 0;
+    if (mat.type != MAT_DIFFUSE_LIGHT) {          // diffuse_light::scatter returns before touching its outputs
+        o.attenuation[0] = att.x; o.attenuation[1] = att.y; o.attenuation[2] = att.z;
+        o.origin[0] = sc.o.x; o.origin[1] = sc.o.y; o.origin[2] = sc.o.z;
+        o.direction[0] = sc.d.x; o.direction[1] = sc.d.y; o.direction[2] = sc.d.z;
+        o.time = sc.tm;
+    }
+    out[i] = o;
+}
+
+__global__ void k_camera_rays(CameraParams cam, const double* st, const double* xi, uint64_t n, double* rays_out)
+{
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XiTable g{ xi + i * 3 };
+    const DRay r = camera_ray(cam, st[i * 2], st[i * 2 + 1], g);
+    double* o = rays_out + i * 7;
+    o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z; o[6] = r.tm;
+}
+
 // counters of one chunk of artb_trace_batch: {n, traverse cursor, -, overflow count}
 __global__ void k_batch_counters(uint32_t* ctr, uint32_t n)
 {
@@ -1476,6 +1532,62 @@ void Renderer::trace_batch(const double* rays_host, uint64_t n, double t_min, do
         }
         trace_batch_device(d_rays, n, t_min, t_max, d_xi, d_out);
         CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, n * sizeof(HitRecordOut), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (...) {
+        for (void* p : bag) cudaFree(p);
+        throw;
+    }
+    for (void* p : bag) cudaFree(p);
+}
+
+void Renderer::shade_batch(const double* rays_host, const int32_t* prim_id_host, const double* t_host, const double* xi_host,
+                           uint64_t n, ShadeRecordOut* out_host)
+{
+    if (!has_scene_) throw std::runtime_error("shade_batch: no scene uploaded");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    std::vector<void*> bag;
+    try {
+        double* d_rays = dev_alloc<double>(bag, n * 7);
+        int32_t* d_id = dev_alloc<int32_t>(bag, n);
+        double* d_t = dev_alloc<double>(bag, n);
+        double* d_xi = dev_alloc<double>(bag, n * 4);
+        ShadeRecordOut* d_out = dev_alloc<ShadeRecordOut>(bag, n);
+        const uint32_t map_size = max_dfs_id_ + 1u;
+        int32_t* d_map = dev_alloc<int32_t>(bag, map_size);
+        CUDA_CHECK(cudaMemcpyAsync(d_rays, rays_host, n * 7 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_id, prim_id_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_t, t_host, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_xi, xi_host, n * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(d_map, 0xff, size_t(map_size) * sizeof(int32_t), st));
+        k_dfs_map<<<(view_.n_world_prims + 255) / 256, 256, 0, st>>>(view_.prims, view_.n_world_prims, d_map, map_size);
+        k_shade_batch<<<unsigned((n + 127) / 128), 128, 0, st>>>(view_, d_rays, d_id, d_t, d_xi, d_map, map_size, n, d_out);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(out_host, d_out, n * sizeof(ShadeRecordOut), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } catch (...) {
+        for (void* p : bag) cudaFree(p);
+        throw;
+    }
+    for (void* p : bag) cudaFree(p);
+}
+
+void Renderer::camera_rays(const CameraParams& cam, const double* st_host, const double* xi_host, uint64_t n, double* rays_out_host)
+{
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    std::vector<void*> bag;
+    try {
+        double* d_st = dev_alloc<double>(bag, n * 2);
+        double* d_xi = dev_alloc<double>(bag, n * 3);
+        double* d_out = dev_alloc<double>(bag, n * 7);
+        CUDA_CHECK(cudaMemcpyAsync(d_st, st_host, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(d_xi, xi_host, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_camera_rays<<<unsigned((n + 127) / 128), 128, 0, st>>>(cam, d_st, d_xi, n, d_out);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpyAsync(rays_out_host, d_out, n * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
     } catch (...) {
         for (void* p : bag) cudaFree(p);

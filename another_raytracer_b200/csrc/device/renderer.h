@@ -76,6 +76,15 @@ public:
     float trace_batch_device(const double* rays_dev, uint64_t n, double t_min, double t_max, const double* xi_dev,
                              HitRecordOut* out_dev);
 
+    // parity hook for the shade stage: hit record + material::emitted / scatter + texture::value for explicit hits
+    // (prim_id = depth-first leaf id and t as trace_batch reports them) with explicit random numbers: xi = n*4 doubles,
+    // consumed in the order the device samplers draw them. Host pointers.
+    void shade_batch(const double* rays_host, const int32_t* prim_id_host, const double* t_host, const double* xi_host,
+                     uint64_t n, ShadeRecordOut* out_host);
+    // parity hook for _stochastic_sample + camera::get_ray: st = n*2 image-plane coordinates (s, t), xi = n*3 doubles
+    // (lens disk radius, lens disk angle, shutter time); rays_out = n*7 doubles. Host pointers.
+    void camera_rays(const CameraParams& cam, const double* st_host, const double* xi_host, uint64_t n, double* rays_out_host);
+
     // Wavefront render into a device accumulation buffer (W*H*3 float sums) + per-pixel sample counts.
     void render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
                        RenderStats* stats, bool profile);

@@ -22,7 +22,7 @@
 namespace artb {
 
 #define ARTB_STACK_DEPTH 32          // uint2 entries; at most 2 per level of 8-wide nodes
-#define ARTB_MAX_BVH8_DEPTH 14
+// ARTB_MAX_BVH8_DEPTH (14 levels): include/artb_flat.h — the limit is part of the ABI
 
 // optional work counters (hostsim / instrumented builds): node visits, primitive tests, medium tests
 struct TraversalStats { unsigned long long nodes, prims, media; };

@@ -193,7 +193,15 @@ __device__ inline d3 texture_value(const SceneView& s, uint32_t tex, double u, d
 }
 
 // ---- sampling -------------------------------------------------------------------------------------
-__device__ __forceinline__ d3 sample_unit_sphere(Philox& g)
+// Random source of the samplers below: the Philox stream of a path (rt_math.cuh), or an explicit table of numbers —
+// the parity hooks artb_shade_batch / artb_camera_rays feed the SAME xi to the device and to the oracle.
+struct XiTable {
+    const double* p;
+    __device__ __forceinline__ double next_double() { return *p++; }
+};
+
+template <class Rng>
+__device__ __forceinline__ d3 sample_unit_sphere(Rng& g)
 {
     const double z = 1.0 - 2.0 * g.next_double();
     const double rxy = sqrt(fmax(0.0, 1.0 - z * z));
@@ -202,13 +210,15 @@ __device__ __forceinline__ d3 sample_unit_sphere(Philox& g)
     return mk3(rxy * cs, rxy * sn, z);
 }
 
-__device__ __forceinline__ d3 sample_unit_ball(Philox& g)
+template <class Rng>
+__device__ __forceinline__ d3 sample_unit_ball(Rng& g)
 {
     const d3 dir = sample_unit_sphere(g);
     return cbrt(g.next_double()) * dir;
 }
 
-__device__ __forceinline__ void sample_unit_disk(Philox& g, double& x, double& y)
+template <class Rng>
+__device__ __forceinline__ void sample_unit_disk(Rng& g, double& x, double& y)
 {
     const double r = sqrt(g.next_double());
     double sn, cs;
@@ -235,8 +245,9 @@ __device__ __forceinline__ d3 material_emitted(const SceneView& s, const FlatMat
 }
 
 // material::scatter (material.h:25-39, 49-56, 67-87, 106-110, 125-131); false = path ends here
+template <class Rng>
 __device__ inline bool material_scatter(const SceneView& s, const FlatMaterial& m, const DRay& r_in, const HitInfo& h,
-                                        Philox& g, d3& attenuation, DRay& scattered)
+                                        Rng& g, d3& attenuation, DRay& scattered)
 {
     scattered.o = h.p;
     scattered.tm = r_in.tm;
@@ -283,7 +294,8 @@ __device__ inline bool material_scatter(const SceneView& s, const FlatMaterial& 
 }
 
 // camera::get_ray (camera.h:38-47) for image-plane coordinates (s,t)
-__device__ __forceinline__ DRay camera_ray(const CameraParams& c, double sx, double ty, Philox& g)
+template <class Rng>
+__device__ __forceinline__ DRay camera_ray(const CameraParams& c, double sx, double ty, Rng& g)
 {
     double dx, dy;
     sample_unit_disk(g, dx, dy);

@@ -2,6 +2,7 @@
 
 #include "artb_tokens.h"
 
+#include <map>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -159,6 +160,190 @@ std::vector<double> dump_graph(const hittable_list& world)
     writer w;
     w.list(world);
     return std::move(w.out);
+}
+
+namespace {
+
+struct reader {
+    const double* t;
+    size_t n, pos = 0;
+    const GraphBlob* blobs;
+    size_t n_blobs;
+    // equal token sequences -> one shared object
+    std::map<std::vector<double>, std::shared_ptr<material>> materials;
+    std::map<std::vector<double>, std::shared_ptr<texture>> textures;
+    std::unordered_map<std::uint64_t, std::shared_ptr<image_texture>> images;
+    int depth = 0;
+
+    double get()
+    {
+        if (pos >= n) throw std::logic_error("graph import: token stream ends early");
+        return t[pos++];
+    }
+    int code()
+    {
+        const double d = get();
+        if (!(d >= 0 && d < 1000) || d != double(int(d))) throw std::logic_error("graph import: bad token");
+        return int(d);
+    }
+    vec3 v3() { const double x = get(), y = get(), z = get(); return vec3(x, y, z); }
+    std::uint64_t hash()
+    {
+        const double lo = get(), hi = get();
+        if (!(lo >= 0 && lo < 4294967296.0 && hi >= 0 && hi < 4294967296.0)) throw std::logic_error("graph import: bad hash");
+        return std::uint64_t(lo) | (std::uint64_t(hi) << 32);
+    }
+    const GraphBlob& blob(std::uint64_t h, std::uint64_t bytes)
+    {
+        for (size_t i = 0; i < n_blobs; ++i)
+            if (blobs[i].hash == h) {
+                if (blobs[i].bytes != bytes || !blobs[i].data) throw std::logic_error("graph import: blob has the wrong size");
+                if (fnv1a64(blobs[i].data, size_t(bytes)) != h) throw std::logic_error("graph import: blob does not match its hash");
+                return blobs[i];
+            }
+        throw std::logic_error("graph import: missing blob (Perlin tables / image texels)");
+    }
+    std::shared_ptr<image_texture> image()
+    {
+        if (code() != ARTB_X_IMAGE) throw std::logic_error("graph import: image expected");
+        const int w = int(get()), h = int(get()), bpp = int(get());
+        const std::uint64_t hh = hash();
+        auto it = images.find(hh ^ (std::uint64_t(w) << 40) ^ (std::uint64_t(h) << 20) ^ std::uint64_t(bpp));
+        if (it != images.end()) return it->second;
+        std::shared_ptr<image_texture> im;
+        if (hh == 0 || w <= 0 || h <= 0 || bpp <= 0) {
+            im = std::make_shared<image_texture>(std::vector<unsigned char>(), 0, 0, 0);       // "no data": renders cyan
+        } else {
+            if (bpp < 3 || bpp > 4 || w > 65536 || h > 65536) throw std::logic_error("graph import: unsupported image format");
+            const GraphBlob& b = blob(hh, std::uint64_t(w) * std::uint64_t(h) * std::uint64_t(bpp));
+            const unsigned char* px = static_cast<const unsigned char*>(b.data);
+            im = std::make_shared<image_texture>(std::vector<unsigned char>(px, px + b.bytes), w, h, bpp);
+        }
+        images.emplace(hh ^ (std::uint64_t(w) << 40) ^ (std::uint64_t(h) << 20) ^ std::uint64_t(bpp), im);
+        return im;
+    }
+    std::shared_ptr<texture> tex()
+    {
+        const size_t start = pos;
+        if (++depth > 64) throw std::logic_error("graph import: textures nested too deep");
+        std::shared_ptr<texture> out;
+        const int c = code();
+        switch (c) {
+            case ARTB_X_SOLID: out = std::make_shared<solid_color>(v3()); break;
+            case ARTB_X_CHECKER: { auto e = tex(); auto o = tex(); out = std::make_shared<checker_texture>(e, o); break; }
+            case ARTB_X_NOISE: {
+                const double scale = get();
+                const GraphBlob& b = blob(hash(), 9216);
+                const double* rv = static_cast<const double*>(b.data);
+                const int* perm = reinterpret_cast<const int*>(static_cast<const char*>(b.data) + 256 * 3 * sizeof(double));
+                for (int i = 0; i < 768; ++i) if (perm[i] < 0 || perm[i] > 255) throw std::logic_error("graph import: bad Perlin permutation");
+                out = std::make_shared<noise_texture>(scale, perlin(rv, perm, perm + 256, perm + 512));
+                break;
+            }
+            case ARTB_X_IMAGE: --pos; out = image(); break;
+            case ARTB_X_BARY_IMAGE: {
+                const double ua = get(), va = get(), ub = get(), vb = get(), uc = get(), vc = get();
+                out = std::make_shared<barycentric_image_texture>(std::make_pair(ua, va), std::make_pair(ub, vb), std::make_pair(uc, vc), image());
+                break;
+            }
+            case ARTB_X_BARY: { const vec3 a = v3(), b = v3(), c3 = v3(); out = std::make_shared<barycentric_texture>(a, b, c3); break; }
+            default: throw std::logic_error("graph import: unknown texture token");
+        }
+        --depth;
+        auto ins = textures.emplace(std::vector<double>(t + start, t + pos), out);
+        return ins.first->second;
+    }
+    std::shared_ptr<material> mat()
+    {
+        const size_t start = pos;
+        std::shared_ptr<material> out;
+        switch (code()) {
+            case ARTB_M_LAMBERTIAN: out = std::make_shared<lambertian>(tex()); break;
+            case ARTB_M_METAL: { const vec3 a = v3(); const double f = get(); out = std::make_shared<metal>(a, f); break; }
+            case ARTB_M_DIELECTRIC: out = std::make_shared<dielectric>(get()); break;
+            case ARTB_M_DIFFUSE_LIGHT: out = std::make_shared<diffuse_light>(tex()); break;
+            case ARTB_M_ISOTROPIC: out = std::make_shared<isotropic>(tex()); break;
+            default: throw std::logic_error("graph import: unknown material token");
+        }
+        auto ins = materials.emplace(std::vector<double>(t + start, t + pos), out);
+        return ins.first->second;
+    }
+    hittable_list list()
+    {
+        if (code() != ARTB_T_LIST) throw std::logic_error("graph import: list expected");
+        const double cnt = get();
+        if (!(cnt >= 0 && cnt <= double(n))) throw std::logic_error("graph import: bad list length");
+        hittable_list l;
+        l.objects.reserve(size_t(cnt));
+        for (size_t i = 0; i < size_t(cnt); ++i) l.add(node());
+        return l;
+    }
+    std::shared_ptr<hittable> node()
+    {
+        if (++depth > 4096) throw std::logic_error("graph import: graph nested too deep");
+        std::shared_ptr<hittable> out;
+        const int c = code();
+        switch (c) {
+            case ARTB_T_LIST: --pos; out = std::make_shared<hittable_list>(list()); break;
+            case ARTB_T_BVH: {
+                const vec3 lo = v3(), hi = v3();
+                const bool same = get() != 0;
+                auto l = node();
+                auto r = same ? l : node();
+                out = std::make_shared<bvh_node>(l, r, aabb(lo, hi));
+                break;
+            }
+            case ARTB_T_TRANSLATE: { const vec3 off = v3(); out = std::make_shared<translate>(node(), off); break; }
+            case ARTB_T_ROTATE_Y: {
+                const double sn = get(), cs = get();
+                const bool has = get() != 0;
+                const vec3 lo = v3(), hi = v3();
+                out = std::make_shared<rotate_y>(node(), sn, cs, has, aabb(lo, hi));
+                break;
+            }
+            case ARTB_T_BOX: { const vec3 lo = v3(), hi = v3(); out = std::make_shared<box>(lo, hi, list()); break; }
+            case ARTB_T_SPHERE: { const vec3 cn = v3(); const double r = get(); out = std::make_shared<sphere>(cn, r, mat()); break; }
+            case ARTB_T_MSPHERE: {
+                const vec3 c0 = v3(), c1 = v3();
+                const double t0 = get(), t1 = get(), r = get();
+                out = std::make_shared<moving_sphere>(c0, c1, t0, t1, r, mat());
+                break;
+            }
+            case ARTB_T_XY: case ARTB_T_XZ: case ARTB_T_YZ: {
+                const double a0 = get(), a1 = get(), b0 = get(), b1 = get(), k = get();
+                auto m = mat();
+                if (c == ARTB_T_XY) out = std::make_shared<xy_rect>(a0, a1, b0, b1, k, m);
+                else if (c == ARTB_T_XZ) out = std::make_shared<xz_rect>(a0, a1, b0, b1, k, m);
+                else out = std::make_shared<yz_rect>(a0, a1, b0, b1, k, m);
+                break;
+            }
+            case ARTB_T_TRI: { const vec3 a = v3(), b = v3(), c3 = v3(); out = std::make_shared<triangle>(a, b, c3, mat()); break; }
+            case ARTB_T_MEDIUM: {
+                const double nid = get();
+                auto phase = mat();
+                if (phase->kind() != material_kind::isotropic) throw std::logic_error("graph import: medium without an isotropic phase function");
+                auto cm = std::make_shared<constant_medium>(node(), 1.0, static_cast<const isotropic&>(*phase).albedo);
+                cm->neg_inv_density = nid;
+                cm->phase_function = phase;
+                out = cm;
+                break;
+            }
+            default: throw std::logic_error("graph import: unknown hittable token");
+        }
+        --depth;
+        return out;
+    }
+};
+
+} // namespace
+
+hittable_list build_graph(const double* tokens, size_t n_tokens, const GraphBlob* blobs, size_t n_blobs)
+{
+    if (!tokens || n_tokens < 2) throw std::logic_error("graph import: empty token stream");
+    reader r{ tokens, n_tokens, 0, blobs, n_blobs };
+    hittable_list world = r.list();
+    if (r.pos != n_tokens) throw std::logic_error("graph import: trailing tokens");
+    return world;
 }
 
 } // namespace artb

@@ -18,6 +18,14 @@ rng_state& global_rng()
 void reset_global_rng(std::uint32_t seed) { global_rng().reseed(seed); }
 
 // ---- textures ----------------------------------------------------------------------------------
+perlin::perlin(const double* ranvec_xyz, const int* px, const int* py, const int* pz)
+{
+    for (int i = 0; i < point_count; ++i) {
+        ranvec[size_t(i)] = vec3(ranvec_xyz[3 * i], ranvec_xyz[3 * i + 1], ranvec_xyz[3 * i + 2]);
+        perm_x[size_t(i)] = px[i]; perm_y[size_t(i)] = py[i]; perm_z[size_t(i)] = pz[i];
+    }
+}
+
 perlin::perlin()
 {
     // reference: perlin.h:10-19 — gradients first, then the x, y, z permutations

@@ -60,6 +60,8 @@ class perlin {
 public:
     static constexpr int point_count = 256;
     perlin();
+    // tables taken as they are (a graph imported from a foreign host: no draws from the global stream)
+    perlin(const double* ranvec_xyz, const int* px, const int* py, const int* pz);
     std::array<vec3, point_count> ranvec;
     std::array<int, point_count> perm_x, perm_y, perm_z;
 private:
@@ -69,6 +71,7 @@ private:
 class noise_texture final : public texture {
 public:
     noise_texture(double sc) : scale(sc) {}
+    noise_texture(double sc, const perlin& tables) : noise(tables), scale(sc) {}
     texture_kind kind() const override { return texture_kind::noise; }
     perlin noise;
     double scale;
@@ -196,6 +199,8 @@ class bvh_node final : public hittable {
 public:
     bvh_node(const hittable_list& list, double time0, double time1);
     bvh_node(std::vector<std::shared_ptr<hittable>>& objects, size_t start, size_t end, double time0, double time1);
+    // an existing node taken as it is (imported graph): no sort, no draw from the global stream
+    bvh_node(std::shared_ptr<hittable> l, std::shared_ptr<hittable> r, const aabb& b) : left(std::move(l)), right(std::move(r)), box(b) {}
 
     hittable_kind kind() const override { return hittable_kind::bvh; }
     bool bounding_box(double, double, aabb& output_box) const override { output_box = box; return true; }
@@ -218,6 +223,8 @@ public:
 class rotate_y final : public hittable {
 public:
     rotate_y(std::shared_ptr<hittable> p, double angle);
+    rotate_y(std::shared_ptr<hittable> p, double sin_t, double cos_t, bool has, const aabb& b)     // imported graph
+        : ptr(std::move(p)), sin_theta(sin_t), cos_theta(cos_t), hasbox(has), bbox(b) {}
     hittable_kind kind() const override { return hittable_kind::rotate_y; }
     bool bounding_box(double, double, aabb& output_box) const override { output_box = bbox; return hasbox; }
     std::shared_ptr<hittable> ptr;
@@ -287,6 +294,7 @@ public:
 class box final : public hittable {
 public:
     box(const point3& p0, const point3& p1, std::shared_ptr<material> ptr);
+    box(const point3& p0, const point3& p1, hittable_list six_sides) : box_min(p0), box_max(p1), sides(std::move(six_sides)) {}   // imported graph
     hittable_kind kind() const override { return hittable_kind::box; }
     bool bounding_box(double, double, aabb& b) const override { b = aabb(box_min, box_max); return true; }
     point3 box_min, box_max;

@@ -19,6 +19,9 @@ from . import _abi
 HIT_DTYPE = np.dtype([("t", "<f8"), ("p", "<f8", 3), ("normal", "<f8", 3), ("u", "<f8"), ("v", "<f8"),
                       ("hit", "<i4"), ("prim_id", "<i4"), ("front_face", "<i4"), ("material_type", "<i4")])
 assert HIT_DTYPE.itemsize == C.sizeof(_abi.Hit)
+SHADE_DTYPE = np.dtype([("emitted", "<f8", 3), ("attenuation", "<f8", 3), ("origin", "<f8", 3), ("direction", "<f8", 3),
+                        ("time", "<f8"), ("scattered", "<i4"), ("material_type", "<i4"), ("front_face", "<i4"), ("reserved", "<i4")])
+assert SHADE_DTYPE.itemsize == C.sizeof(_abi.ShadeRecord)
 
 MATERIAL_NAMES = ["lambertian", "metal", "dielectric", "diffuse_light", "isotropic"]
 
@@ -63,6 +66,28 @@ def _check(rc: int, ctx=None):
         raise ArtbError(rc, (msg or b"").decode(errors="replace"))
 
 
+def read_graph_file(path):
+    """(tokens, {hash: bytes}, background) of an exported scene graph: int64 header {'ARTG', 1, n_tokens, n_blobs, 0, 0},
+    background (3 doubles), tokens, then per blob hash + byte count (uint64) + bytes padded to a multiple of 8"""
+    raw = open(path, "rb").read()
+    hdr = np.frombuffer(raw, dtype="<i8", count=6)
+    if hdr[0] != 0x47545241 or hdr[1] != 1:
+        raise ValueError(f"{path}: not an exported scene graph")
+    n_tokens, n_blobs = int(hdr[2]), int(hdr[3])
+    background = np.frombuffer(raw, dtype="<f8", count=3, offset=48).copy()
+    tokens = np.frombuffer(raw, dtype="<f8", count=n_tokens, offset=72).copy()
+    off = 72 + 8 * n_tokens
+    blobs = {}
+    for _ in range(n_blobs):
+        h, nbytes = (int(x) for x in np.frombuffer(raw, dtype="<u8", count=2, offset=off))
+        off += 16
+        blobs[h] = raw[off:off + nbytes]
+        off += (nbytes + 7) // 8 * 8
+    if off != len(raw):
+        raise ValueError(f"{path}: trailing bytes")
+    return tokens, blobs, background
+
+
 class Scene:
     """A host scene graph built by the C++ scene_manager mirror, plus its flattened arrays."""
 
@@ -84,6 +109,29 @@ class Scene:
         h = C.c_void_p()
         _check(lib.artb_scene_build(int(alias), C.byref(opt), C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def from_graph(cls, tokens: np.ndarray, blobs: dict, background, max_leaf_prims: int = 0, device_bvh: bool = False) -> "Scene":
+        """artb_scene_from_graph: a scene graph built by a foreign host (the reference's own hittable_list serialised by
+        include/artb_reference_adapter.hpp). tokens: the stream of artb_tokens.h; blobs: {hash: bytes} of the Perlin
+        tables / image texels the stream names."""
+        lib = _abi.load()
+        tokens = np.ascontiguousarray(tokens, dtype=np.float64)
+        keep = [np.frombuffer(b, dtype=np.uint8) for b in blobs.values()]
+        table = (_abi.GraphBlob * max(len(blobs), 1))()
+        for i, (h, a) in enumerate(zip(blobs.keys(), keep)):
+            table[i] = _abi.GraphBlob(int(h), a.ctypes.data, a.size)
+        bg = (C.c_double * 3)(*background)
+        opt = _abi.SceneOptions(0, 0, int(max_leaf_prims), int(device_bvh), None)
+        h = C.c_void_p()
+        _check(lib.artb_scene_from_graph(tokens.ctypes.data, tokens.size, table, len(blobs), C.byref(bg), C.byref(opt), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_graph_file(cls, path, **kw) -> "Scene":
+        """the container file artb_ref::exporter::write_file writes (include/artb_reference_adapter.hpp)"""
+        tokens, blobs, background = read_graph_file(path)
+        return cls.from_graph(tokens, blobs, background, **kw)
 
     def dump_graph(self) -> np.ndarray:
         lib = _abi.load()
@@ -194,6 +242,28 @@ class Context:
             medium_xi = np.ascontiguousarray(medium_xi, dtype=np.float64).reshape(n, self.n_media)
             xi_ptr = medium_xi.ctypes.data
         _check(self._lib.artb_trace_batch(self._h, rays.ctypes.data, n, t_min, t_max, xi_ptr, out.ctypes.data), self._h)
+        return out
+
+    def shade_batch(self, rays: np.ndarray, prim_id: np.ndarray, t: np.ndarray, xi: np.ndarray) -> np.ndarray:
+        """artb_shade_batch: material::emitted / scatter of explicit hits with explicit random numbers (n x 4)"""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = rays.shape[0]
+        prim_id = np.ascontiguousarray(prim_id, dtype=np.int32).reshape(n)
+        t = np.ascontiguousarray(t, dtype=np.float64).reshape(n)
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(n, 4)
+        out = np.zeros(n, dtype=SHADE_DTYPE)
+        _check(self._lib.artb_shade_batch(self._h, rays.ctypes.data, prim_id.ctypes.data, t.ctypes.data, xi.ctypes.data, n,
+                                          out.ctypes.data), self._h)
+        return out
+
+    def camera_rays(self, cam: "CameraDesc", st: np.ndarray, xi: np.ndarray) -> np.ndarray:
+        """artb_camera_rays: camera::get_ray for explicit image-plane coordinates (n x 2) and random numbers (n x 3)"""
+        st = np.ascontiguousarray(st, dtype=np.float64).reshape(-1, 2)
+        n = st.shape[0]
+        xi = np.ascontiguousarray(xi, dtype=np.float64).reshape(n, 3)
+        out = np.zeros((n, 7), dtype=np.float64)
+        c = cam.to_c()
+        _check(self._lib.artb_camera_rays(self._h, C.byref(c), st.ctypes.data, xi.ctypes.data, n, out.ctypes.data), self._h)
         return out
 
     def build_bvh_device(self, max_leaf_prims: int = 1) -> dict:

@@ -16,6 +16,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "artb_flat.h"
 #include "artb_tokens.h"
 
 #ifdef __cplusplus
@@ -79,22 +80,34 @@ int artb_scene_get_info(const artb_scene* s, artb_scene_info* out);
 int64_t artb_scene_dump_graph(const artb_scene* s, double* out, int64_t capacity);
 
 /* ---- flattened scene as plain arrays (what a foreign host hands over) ----------------- */
-typedef struct artb_flat_scene {
-    const void* prims;      uint32_t n_prims, n_world_prims;   /* FlatPrim[],   96 B each: globals, BVH leaves, boundaries */
-    const void* nodes;      uint32_t n_nodes; int32_t reserved0; uint32_t n_global_prims; int32_t bvh_depth;   /* FlatNode8[], 80 B: 8-wide quantised BVH, [0] = root */
-    const void* xform_ops;  uint32_t n_xform_ops;              /* FlatXformOp[], 32 B      */
-    const void* xforms;     uint32_t n_xforms;                 /* FlatXform[],    8 B      */
-    const void* materials;  uint32_t n_materials;              /* FlatMaterial[], 48 B     */
-    const void* textures;   uint32_t n_textures;               /* FlatTexture[],  96 B     */
-    const void* images;     uint32_t n_images;                 /* FlatImage[],    24 B     */
-    const unsigned char* texels; uint64_t n_texel_bytes;
-    const void* perlins;    uint32_t n_perlins;                /* FlatPerlin[], 9216 B     */
+typedef struct artb_flat_scene {         /* record types: artb_flat.h */
+    const artb_flat_prim* prims;          uint32_t n_prims, n_world_prims;   /* globals, BVH leaves, then media boundaries */
+    const artb_flat_node8* nodes;         uint32_t n_nodes; int32_t reserved0; uint32_t n_global_prims; int32_t bvh_depth;
+                                          /* [0] = root; n_nodes == 0: the tree is built on the GPU; bvh_depth <= 14 levels */
+    const artb_flat_xform_op* xform_ops;  uint32_t n_xform_ops;
+    const artb_flat_xform* xforms;        uint32_t n_xforms;                 /* [0] = identity */
+    const artb_flat_material* materials;  uint32_t n_materials;
+    const artb_flat_texture* textures;    uint32_t n_textures;
+    const artb_flat_image* images;        uint32_t n_images;
+    const unsigned char* texels;          uint64_t n_texel_bytes;
+    const artb_flat_perlin* perlins;      uint32_t n_perlins;
     uint32_t n_media;
     double background[3];
-    const void* ref_nodes;  uint32_t n_ref_nodes;              /* FlatRefNode[], 64 B: the reference's own bvh_nodes, used only
+    const artb_flat_ref_node* ref_nodes;  uint32_t n_ref_nodes;              /* the reference's own bvh_nodes, used only
                                                                   to break exact-t ties as bvh_node::hit does (may be NULL/0:
-                                                                  ties then go to the larger dfs_id); FlatPrim::g[9] = 1 + index */
+                                                                  ties then go to the larger dfs_id); prim g[9] = 1 + index */
 } artb_flat_scene;
+
+/* A scene graph built by a FOREIGN host (the reference's own hittable_list): `tokens` is its pre-order serialisation
+ * (artb_tokens.h; include/artb_reference_adapter.hpp writes it from the reference's classes, reference:
+ * src/engine/hittable_list.h:9-24, src/primitives/bvh.h:9-26, ...), `blobs` the Perlin tables / image texels the stream
+ * names by hash. The graph is rebuilt as it is (the reference's bvh_node shapes and boxes included: they decide culling
+ * and exact-tie order) and flattened; nothing is drawn from the RNG. opt may be NULL (mesh_as_soup / heightfield_side /
+ * assets_root are ignored). The result is an ordinary artb_scene: artb_upload_scene, or artb_scene_get_flat +
+ * artb_upload_flat. lookfrom / lookat / vfov of artb_scene_info are zero: the caller owns the camera. */
+typedef struct artb_graph_blob { uint64_t hash; const void* data; uint64_t bytes; } artb_graph_blob;
+int artb_scene_from_graph(const double* tokens, int64_t n_tokens, const artb_graph_blob* blobs, int32_t n_blobs,
+                          const double background[3], const artb_scene_options* opt, artb_scene** out);
 
 /* view of the arrays owned by `s` (valid until artb_scene_free) */
 int artb_scene_get_flat(const artb_scene* s, artb_flat_scene* out);
@@ -135,6 +148,32 @@ int artb_last_bvh_build(const artb_ctx* ctx, artb_bvh_stats* stats);
 /* how many rays of the last artb_trace_batch* call took the one-phase overflow pass instead of the pair kernels
  * (0 for the reference's scenes; the tests assert it so that parity is known to cover the kernels the renderer runs) */
 uint64_t artb_trace_overflow_rays(const artb_ctx* ctx);
+
+/* ---- parity hooks for the shade stage ------------------------------------------------------------------
+ * material::emitted / material::scatter / texture::value (material.h:10-135, texture.h:16-154, perlin.h:21-96) and
+ * camera::get_ray (camera.h:38-47) are deterministic once the random numbers they consume are given. These two
+ * calls run the device functions the render kernels run, on explicit inputs with EXPLICIT random numbers, so the
+ * shade stage can be compared with the oracle value by value (like artb_trace_batch does for the hit stage). The
+ * device draws unit-sphere / unit-ball / unit-disk samples in closed form (same distributions as the reference's
+ * rejection loops, vec3.h:117-143); xi are consumed in this order:
+ *   lambertian  z = 1-2*xi0, phi = 2*pi*xi1                     metal / isotropic  the same + radius cbrt(xi2)
+ *   dielectric  xi0 against the Schlick reflectance (only when refraction is possible)
+ *   camera      lens radius sqrt(xi0), lens angle 2*pi*xi1, time = time0 + (time1-time0)*xi2                     */
+typedef struct artb_shade_record {
+    double emitted[3];                  /* material::emitted(u, v, p) */
+    double attenuation[3];              /* scatter()'s attenuation */
+    double origin[3], direction[3], time;   /* scatter()'s scattered ray */
+    int32_t scattered;                  /* scatter()'s return value; -1: prim_id does not name a primitive */
+    int32_t material_type, front_face, reserved;
+} artb_shade_record;
+
+/* rays: n x 7 doubles; prim_id / t: the hit as artb_trace_batch reported it; xi: n x 4 doubles. HOST pointers. */
+int artb_shade_batch(artb_ctx* ctx, const double* rays, const int32_t* prim_id, const double* t, const double* xi,
+                     uint64_t n, artb_shade_record* out);
+struct artb_camera;
+/* st: n x 2 image-plane coordinates (s, t) as engine.h:62-63 computes them; xi: n x 3; rays_out: n x 7. HOST pointers. */
+int artb_camera_rays(artb_ctx* ctx, const struct artb_camera* cam, const double* st, const double* xi, uint64_t n,
+                     double* rays_out);
 
 /* ---- engine::run (engine.h:30-54) ------------------------------------------------------------------ */
 typedef struct artb_camera {            /* camera::camera arguments, camera.h:8-17 */

@@ -438,11 +438,49 @@ color emitted(const material& m, double u, double v, const point3& p)
     return color(0, 0, 0);
 }
 
-bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& attenuation, ray& scattered)
+// Where scatter() and get_ray() take their random points from. ref_sampler: the reference's rejection loops on the
+// global MT19937 stream (vec3.h:117-143) — what every pinned test and every render uses. xi_sampler: explicit numbers
+// through the closed forms the DEVICE uses (rt_shade.cuh: same distributions), for the value-by-value shade parity
+// hooks oracle_shade / oracle_camera_rays: both sides then evaluate the same expressions on the same xi.
+struct ref_sampler {
+    vec3 unit_vector_on_sphere() { return random_unit_vector(); }
+    vec3 in_unit_sphere() { return random_in_unit_sphere(); }
+    vec3 in_unit_disk() { return random_in_unit_disk(); }
+    double uniform() { return random_double(); }
+    double uniform(double a, double b) { return random_double(a, b); }
+};
+
+struct xi_sampler {
+    const double* xi;
+    double next() { return *xi++; }
+    vec3 unit_vector_on_sphere()
+    {
+        const double z = 1.0 - 2.0 * next();
+        const double rxy = std::sqrt(std::max(0.0, 1.0 - z * z));
+        const double phi = 2.0 * next();                       // in units of pi, like sincospi on the device
+        return vec3(rxy * std::cos(pi * phi), rxy * std::sin(pi * phi), z);
+    }
+    vec3 in_unit_sphere()
+    {
+        const vec3 dir = unit_vector_on_sphere();
+        return std::cbrt(next()) * dir;
+    }
+    vec3 in_unit_disk()
+    {
+        const double r = std::sqrt(next());
+        const double phi = 2.0 * next();
+        return vec3(r * std::cos(pi * phi), r * std::sin(pi * phi), 0);
+    }
+    double uniform() { return next(); }
+    double uniform(double a, double b) { return a + (b - a) * next(); }      // tracer_utils.h:33-35
+};
+
+template <class Sampler>
+bool scatter_with(const material& m, const ray& r_in, const hit_record& rec, color& attenuation, ray& scattered, Sampler& smp)
 {
     switch (m.kind()) {
         case material_kind::lambertian: {
-            vec3 scatter_direction = rec.normal + random_unit_vector();
+            vec3 scatter_direction = rec.normal + smp.unit_vector_on_sphere();
             if (scatter_direction.near_zero()) scatter_direction = rec.normal;
             scattered = ray(rec.p, scatter_direction, r_in.time());
             attenuation = texture_value(*static_cast<const lambertian&>(m).albedo, rec.u, rec.v, rec.p);
@@ -451,7 +489,7 @@ bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& a
         case material_kind::metal: {
             const auto& me = static_cast<const metal&>(m);
             const vec3 reflected = reflect(unit_vector(r_in.direction()), rec.normal);
-            scattered = ray(rec.p, reflected + me.fuzz * random_in_unit_sphere(), r_in.time());
+            scattered = ray(rec.p, reflected + me.fuzz * smp.in_unit_sphere(), r_in.time());
             attenuation = me.albedo;
             return dot(scattered.direction(), rec.normal) > 0;
         }
@@ -469,7 +507,7 @@ bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& a
                 r0 = r0 * r0;
                 return r0 + (1 - r0) * std::pow((1 - cosine), 5);
             };
-            if (cannot_refract || reflectance(cos_theta, refraction_ratio) > random_double())
+            if (cannot_refract || reflectance(cos_theta, refraction_ratio) > smp.uniform())
                 direction = reflect(unit_direction, rec.normal);
             else
                 direction = refract(unit_direction, rec.normal, refraction_ratio);
@@ -478,7 +516,7 @@ bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& a
         }
         case material_kind::diffuse_light: return false;
         case material_kind::isotropic: {
-            scattered = ray(rec.p, random_in_unit_sphere(), r_in.time());
+            scattered = ray(rec.p, smp.in_unit_sphere(), r_in.time());
             attenuation = texture_value(*static_cast<const isotropic&>(m).albedo, rec.u, rec.v, rec.p);
             return true;
         }
@@ -486,13 +524,26 @@ bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& a
     return false;
 }
 
+bool scatter(const material& m, const ray& r_in, const hit_record& rec, color& attenuation, ray& scattered)
+{
+    ref_sampler smp;
+    return scatter_with(m, r_in, rec, attenuation, scattered, smp);
+}
+
 // camera::get_ray: camera.h:38-47
+template <class Sampler>
+ray get_ray_with(const camera& c, double s, double t, Sampler& smp)
+{
+    const vec3 rd = c.lens_radius * smp.in_unit_disk();
+    const vec3 offset = c.u * rd.x() + c.v * rd.y();
+    const double tm = smp.uniform(c.time0, c.time1);
+    return ray(c.origin + offset, c.lower_left_corner + s * c.horizontal + t * c.vertical - c.origin - offset, tm);
+}
+
 ray get_ray(const camera& c, double s, double t)
 {
-    const vec3 rd = c.lens_radius * random_in_unit_disk();
-    const vec3 offset = c.u * rd.x() + c.v * rd.y();
-    const double tm = random_double(c.time0, c.time1);
-    return ray(c.origin + offset, c.lower_left_corner + s * c.horizontal + t * c.vertical - c.origin - offset, tm);
+    ref_sampler smp;
+    return get_ray_with(c, s, t, smp);
 }
 
 // optional log of every closest-hit query of a render (origin, direction, time, remaining depth): lets the tests and
@@ -641,6 +692,84 @@ ORACLE_API int oracle_trace(void* h, const double* rays, std::uint64_t n, double
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "oracle_trace: %s\n", e.what());
+        return -1;
+    }
+}
+
+// Shade-stage parity hook (the counterpart of artb_shade_batch): closest hit of every ray with the reference's
+// algorithm (medium_xi as in oracle_trace), then material::emitted and material::scatter of that hit with the random
+// numbers xi4[i*4..] fed through the device's closed-form samplers (xi_sampler above).
+struct oracle_shade_record {
+    double emitted[3], attenuation[3], origin[3], direction[3], time;
+    std::int32_t scattered, material_type, front_face, prim_id;      // prim_id = the hit's leaf id (-1: miss, record is zero)
+};
+
+ORACLE_API int oracle_shade(void* h, const double* rays, std::uint64_t n, const double* medium_xi, const double* xi4,
+                            oracle_hit* hits_out, oracle_shade_record* out)
+{
+    try {
+        auto* o = static_cast<oracle_scene*>(h);
+        for (std::uint64_t i = 0; i < n; ++i) {
+            const double* r7 = rays + i * 7;
+            const ray r(point3(r7[0], r7[1], r7[2]), vec3(r7[3], r7[4], r7[5]), r7[6]);
+            query_ctx q;
+            q.leaf_ids = &o->leaf_ids;
+            q.medium_slots = &o->medium_slots;
+            q.xi_row = medium_xi ? medium_xi + i * std::uint64_t(o->n_media) : nullptr;
+            hit_record rec;
+            const bool ok = hit_any(o->s.objects, r, 0.001, infinity, rec, q);
+            oracle_shade_record& w = out[i];
+            std::memset(&w, 0, sizeof(w));
+            w.prim_id = ok ? q.last_leaf : -1;
+            w.material_type = -1;
+            if (hits_out) {
+                oracle_hit& hh = hits_out[i];
+                std::memset(&hh, 0, sizeof(hh));
+                hh.hit = ok ? 1 : 0; hh.prim_id = w.prim_id; hh.material_type = ok ? material_code(rec.mat_ptr) : -1;
+                if (ok) {
+                    hh.t = rec.t; hh.u = rec.u; hh.v = rec.v; hh.front_face = rec.front_face ? 1 : 0;
+                    for (int k = 0; k < 3; ++k) { hh.p[k] = rec.p[k]; hh.normal[k] = rec.normal[k]; }
+                }
+            }
+            if (!ok) continue;
+            w.material_type = material_code(rec.mat_ptr);
+            w.front_face = rec.front_face ? 1 : 0;
+            const color e = emitted(*rec.mat_ptr, rec.u, rec.v, rec.p);
+            xi_sampler smp{ xi4 + i * 4 };
+            color att(0, 0, 0);
+            ray sc;
+            const bool s_ok = scatter_with(*rec.mat_ptr, r, rec, att, sc, smp);
+            w.scattered = s_ok ? 1 : 0;
+            for (int k = 0; k < 3; ++k) w.emitted[k] = e[k];
+            if (rec.mat_ptr->kind() != material_kind::diffuse_light) {
+                for (int k = 0; k < 3; ++k) { w.attenuation[k] = att[k]; w.origin[k] = sc.origin()[k]; w.direction[k] = sc.direction()[k]; }
+                w.time = sc.time();
+            }
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "oracle_shade: %s\n", e.what());
+        return -1;
+    }
+}
+
+// camera::camera + camera::get_ray (camera.h:8-47) for explicit (s, t) and xi3 = (disk radius, disk angle, time)
+ORACLE_API int oracle_camera_rays(const double* cam9, double vfov, double aspect, double aperture, double focus_dist, double time0,
+                                  double time1, const double* st, const double* xi3, std::uint64_t n, double* rays_out)
+{
+    try {
+        const camera cam(point3(cam9[0], cam9[1], cam9[2]), point3(cam9[3], cam9[4], cam9[5]), vec3(cam9[6], cam9[7], cam9[8]), vfov,
+                         aspect, aperture, focus_dist, time0, time1);
+        for (std::uint64_t i = 0; i < n; ++i) {
+            xi_sampler smp{ xi3 + i * 3 };
+            const ray r = get_ray_with(cam, st[i * 2], st[i * 2 + 1], smp);
+            double* w = rays_out + i * 7;
+            for (int k = 0; k < 3; ++k) { w[k] = r.origin()[k]; w[3 + k] = r.direction()[k]; }
+            w[6] = r.time();
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "oracle_camera_rays: %s\n", e.what());
         return -1;
     }
 }

@@ -5,6 +5,8 @@
 //   rng N                         first N values of the reference's global RNG (tracer_utils.h:27-31)
 //   info ALIAS                    scene statistics + next RNG value after scene_manager::build
 //   graph ALIAS OUT               pre-order dump of the built scene graph (include/artb_tokens.h)
+//   export ALIAS OUT              the same stream + the payloads it names (Perlin tables, texels) in the container
+//                                 format of include/artb_reference_adapter.hpp: input of artb_scene_from_graph
 //   trace ALIAS W H STRIDE SPP MAX OUT   every closest-hit query (engine.h:455) made while path tracing
 //                                 a sparse pixel grid: ray, hit record, winning leaf id, media xi
 //   render ALIAS W H SPP OUT [BURN]      single-mode render with runtime W/H/spp (restates the three
@@ -28,6 +30,8 @@
 #include "ref_scenes.h"
 
 #include "artb_tokens.h"
+#define ARTB_REF_ADAPTER_NO_LIBRARY            // ref_tool does not link libartb.so: it only writes files
+#include "artb_reference_adapter.hpp"
 
 #include <cinttypes>
 #include <cstdio>
@@ -41,134 +45,12 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// graph dump
+// graph dump / export: include/artb_reference_adapter.hpp — the SAME walker a reference maintainer would use to hand the
+// reference's graph to the backend; `graph` writes its token stream (pinned by tests/golden/scene_info.json),
+// `export` the container file (tokens + Perlin / texel payloads) that artb_scene_from_graph consumes
 // ------------------------------------------------------------------------------------------------
-std::uint64_t fnv1a(const void* data, size_t n, std::uint64_t h = 1469598103934665603ULL)
-{
-    const unsigned char* p = static_cast<const unsigned char*>(data);
-    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
-    return h;
-}
-
-struct dumper
-{
-    std::vector<double> out;
-    std::map<std::string,int> counts;
-    int max_depth = 0;
-    int bvh_nodes = 0, bvh_single = 0;
-
-    void v3(const vec3& v) { out.push_back(v.x()); out.push_back(v.y()); out.push_back(v.z()); }
-    void hash(std::uint64_t h) { out.push_back(double(h & 0xffffffffULL)); out.push_back(double(h >> 32)); }
-
-    void tex(const std::shared_ptr<texture>& t)
-    {
-        if (auto s = std::dynamic_pointer_cast<solid_color>(t)) {
-            out.push_back(ARTB_X_SOLID); v3(s->color_value);
-        } else if (auto c = std::dynamic_pointer_cast<checker_texture>(t)) {
-            out.push_back(ARTB_X_CHECKER); tex(c->even); tex(c->odd);
-        } else if (auto n = std::dynamic_pointer_cast<noise_texture>(t)) {
-            out.push_back(ARTB_X_NOISE); out.push_back(n->scale);
-            std::uint64_t h = fnv1a(n->noise.ranvec.data(), sizeof(vec3) * 256);
-            h = fnv1a(n->noise.perm_x.data(), sizeof(int) * 256, h);
-            h = fnv1a(n->noise.perm_y.data(), sizeof(int) * 256, h);
-            h = fnv1a(n->noise.perm_z.data(), sizeof(int) * 256, h);
-            hash(h);
-        } else if (auto i = std::dynamic_pointer_cast<image_texture>(t)) {
-            image(i);
-        } else if (auto b = std::dynamic_pointer_cast<barycentric_image_texture>(t)) {
-            out.push_back(ARTB_X_BARY_IMAGE);
-            out.push_back(b->texcoord_a.first); out.push_back(b->texcoord_a.second);
-            out.push_back(b->texcoord_b.first); out.push_back(b->texcoord_b.second);
-            out.push_back(b->texcoord_c.first); out.push_back(b->texcoord_c.second);
-            image(b->tex);
-        } else if (auto bc = std::dynamic_pointer_cast<barycentric_texture>(t)) {
-            out.push_back(ARTB_X_BARY); v3(bc->color_a); v3(bc->color_b); v3(bc->color_c);
-        } else throw std::logic_error("graph dump: unknown texture type");
-    }
-    std::map<const image_texture*, std::uint64_t> image_hashes;   // one image is shared by many triangles
-    void image(const std::shared_ptr<image_texture>& i)
-    {
-        out.push_back(ARTB_X_IMAGE);
-        out.push_back(i->width); out.push_back(i->height); out.push_back(i->bytes_per_pixel);
-        auto it = image_hashes.find(i.get());
-        if (it == image_hashes.end())
-            it = image_hashes.emplace(i.get(), i->data ? fnv1a(i->data.get(), size_t(i->width) * size_t(i->height) * size_t(i->bytes_per_pixel)) : 0).first;
-        hash(it->second);
-    }
-    void mat(const std::shared_ptr<material>& m)
-    {
-        if (auto l = std::dynamic_pointer_cast<lambertian>(m)) {
-            out.push_back(ARTB_M_LAMBERTIAN); tex(l->albedo);
-        } else if (auto me = std::dynamic_pointer_cast<metal>(m)) {
-            out.push_back(ARTB_M_METAL); v3(me->albedo); out.push_back(me->fuzz);
-        } else if (auto d = std::dynamic_pointer_cast<dielectric>(m)) {
-            out.push_back(ARTB_M_DIELECTRIC); out.push_back(d->ir);
-        } else if (auto dl = std::dynamic_pointer_cast<diffuse_light>(m)) {
-            out.push_back(ARTB_M_DIFFUSE_LIGHT); tex(dl->emit);
-        } else if (auto is = std::dynamic_pointer_cast<isotropic>(m)) {
-            out.push_back(ARTB_M_ISOTROPIC); tex(is->albedo);
-        } else throw std::logic_error("graph dump: unknown material type");
-    }
-    void list(const hittable_list& l, int depth)
-    {
-        out.push_back(ARTB_T_LIST); out.push_back(double(l.objects.size()));
-        for (const auto& o : l.objects) node(o, depth + 1);
-    }
-    void node(const std::shared_ptr<hittable>& h, int depth)
-    {
-        max_depth = std::max(max_depth, depth);
-        if (auto l = std::dynamic_pointer_cast<hittable_list>(h)) {
-            counts["list"]++; list(*l, depth);
-        } else if (auto b = std::dynamic_pointer_cast<bvh_node>(h)) {
-            counts["bvh_node"]++; bvh_nodes++;
-            const bool same = b->left.get() == b->right.get();
-            if (same) bvh_single++;
-            out.push_back(ARTB_T_BVH); v3(b->box.min()); v3(b->box.max()); out.push_back(same ? 1 : 0);
-            node(b->left, depth + 1);
-            if (!same) node(b->right, depth + 1);
-        } else if (auto t = std::dynamic_pointer_cast<translate>(h)) {
-            counts["translate"]++;
-            out.push_back(ARTB_T_TRANSLATE); v3(t->offset); node(t->ptr, depth + 1);
-        } else if (auto r = std::dynamic_pointer_cast<rotate_y>(h)) {
-            counts["rotate_y"]++;
-            out.push_back(ARTB_T_ROTATE_Y); out.push_back(r->sin_theta); out.push_back(r->cos_theta);
-            out.push_back(r->hasbox ? 1 : 0); v3(r->bbox.min()); v3(r->bbox.max());
-            node(r->ptr, depth + 1);
-        } else if (auto bx = std::dynamic_pointer_cast<box>(h)) {
-            counts["box"]++;
-            out.push_back(ARTB_T_BOX); v3(bx->box_min); v3(bx->box_max); list(bx->sides, depth + 1);
-        } else if (auto s = std::dynamic_pointer_cast<sphere>(h)) {
-            counts["sphere"]++;
-            out.push_back(ARTB_T_SPHERE); v3(s->center); out.push_back(s->radius); mat(s->mat_ptr);
-        } else if (auto ms = std::dynamic_pointer_cast<moving_sphere>(h)) {
-            counts["moving_sphere"]++;
-            out.push_back(ARTB_T_MSPHERE); v3(ms->center0); v3(ms->center1);
-            out.push_back(ms->time0); out.push_back(ms->time1); out.push_back(ms->radius); mat(ms->mat_ptr);
-        } else if (auto xy = std::dynamic_pointer_cast<xy_rect>(h)) {
-            counts["xy_rect"]++;
-            out.push_back(ARTB_T_XY);
-            for (double d : { xy->x0, xy->x1, xy->y0, xy->y1, xy->k }) out.push_back(d);
-            mat(xy->mp);
-        } else if (auto xz = std::dynamic_pointer_cast<xz_rect>(h)) {
-            counts["xz_rect"]++;
-            out.push_back(ARTB_T_XZ);
-            for (double d : { xz->x0, xz->x1, xz->z0, xz->z1, xz->k }) out.push_back(d);
-            mat(xz->mp);
-        } else if (auto yz = std::dynamic_pointer_cast<yz_rect>(h)) {
-            counts["yz_rect"]++;
-            out.push_back(ARTB_T_YZ);
-            for (double d : { yz->y0, yz->y1, yz->z0, yz->z1, yz->k }) out.push_back(d);
-            mat(yz->mp);
-        } else if (auto tr = std::dynamic_pointer_cast<triangle>(h)) {
-            counts["triangle"]++;
-            out.push_back(ARTB_T_TRI); v3(tr->pt1); v3(tr->pt2); v3(tr->pt3); mat(tr->mat_ptr);
-        } else if (auto cm = std::dynamic_pointer_cast<constant_medium>(h)) {
-            counts["constant_medium"]++;
-            out.push_back(ARTB_T_MEDIUM); out.push_back(cm->neg_inv_density); mat(cm->phase_function);
-            node(cm->boundary, depth + 1);
-        } else throw std::logic_error("graph dump: unknown hittable type");
-    }
-};
+using artb_ref::fnv1a;
+using dumper = artb_ref::exporter;
 
 // ------------------------------------------------------------------------------------------------
 // leaf tagging: each surface leaf and each constant_medium is wrapped by a forwarding
@@ -457,6 +339,18 @@ int cmd_render(int alias, int W, int H, int spp, const char* out, long burn)
     return f.good() ? 0 : 1;
 }
 
+int cmd_export(int alias, const char* out)
+{
+    scene s = build_scene(alias);
+    dumper d;
+    d.list(s.objects);
+    if (!d.write_file(out, s.background)) { std::fprintf(stderr, "cannot write %s\n", out); return 1; }
+    std::printf("{\"alias\": %d, \"tokens\": %zu, \"blobs\": %zu, \"lookfrom\": [%.17g, %.17g, %.17g], \"lookat\": [%.17g, %.17g, %.17g], "
+                "\"vfov\": %.17g, \"aperture\": %.17g}\n", alias, d.out.size(), d.blobs.size(), s.lookfrom.x(), s.lookfrom.y(), s.lookfrom.z(),
+                s.lookat.x(), s.lookat.y(), s.lookat.z(), s.vfov, s.aperture);
+    return 0;
+}
+
 int cmd_decode(const char* in, const char* out)
 {
     int w = 0, h = 0, bpp = 0;
@@ -490,6 +384,7 @@ int main(int argc, char** argv) try
     if (cmd == "rng" && argc >= 3)     return cmd_rng(std::atoi(argv[2]));
     if (cmd == "info" && argc >= 3)    return cmd_info(std::atoi(argv[2]));
     if (cmd == "graph" && argc >= 4)   return cmd_graph(std::atoi(argv[2]), argv[3]);
+    if (cmd == "export" && argc >= 4)  return cmd_export(std::atoi(argv[2]), argv[3]);
     if (cmd == "trace" && argc >= 9)   return cmd_trace(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]),
                                                         std::atoi(argv[5]), std::atoi(argv[6]),
                                                         size_t(std::atoll(argv[7])), argv[8]);

@@ -19,10 +19,10 @@ _lib = None
 def load():
     global _lib
     if _lib is None:
-        deps = [SRC] + sorted(DEVICE_DIR.glob("*.cuh")) + sorted(DEVICE_DIR.glob("*.h"))
+        deps = [SRC] + sorted(DEVICE_DIR.glob("*.cuh")) + sorted(DEVICE_DIR.glob("*.h")) + sorted((HERE.parent / "include").glob("*.h"))
         if not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
             LIB.parent.mkdir(exist_ok=True)
-            subprocess.run(["g++", "-O2", "-std=gnu++17", "-fPIC", "-shared", "-x", "c++", str(SRC), "-o", str(LIB)], check=True)
+            subprocess.run(["g++", "-O2", "-std=gnu++17", "-fPIC", "-shared", f"-I{HERE.parent / 'include'}", "-x", "c++", str(SRC), "-o", str(LIB)], check=True)
         lib = C.CDLL(str(LIB))
         lib.hostsim_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hostsim_trace.restype = C.c_int

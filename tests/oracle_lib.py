@@ -13,6 +13,9 @@ REF_TOOL = ROOT / "oracle" / "_ref" / "ref_tool"
 HIT_DTYPE = np.dtype([("t", "<f8"), ("p", "<f8", 3), ("normal", "<f8", 3), ("u", "<f8"), ("v", "<f8"),
                       ("hit", "<i4"), ("prim_id", "<i4"), ("front_face", "<i4"), ("material_type", "<i4")])
 
+SHADE_DTYPE = np.dtype([("emitted", "<f8", 3), ("attenuation", "<f8", 3), ("origin", "<f8", 3), ("direction", "<f8", 3),
+                        ("time", "<f8"), ("scattered", "<i4"), ("material_type", "<i4"), ("front_face", "<i4"), ("prim_id", "<i4")])
+
 _lib = None
 
 
@@ -33,6 +36,9 @@ def load():
         lib.oracle_rng_burn.argtypes = [C.c_long]
         lib.oracle_rng_reseed.argtypes = [C.c_uint]
         lib.oracle_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_shade.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_camera_rays.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                           C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.POINTER(C.c_uint64)]
         lib.oracle_render.restype = C.c_double
@@ -79,6 +85,33 @@ class OracleScene:
             raise RuntimeError("oracle_render failed")
         return rgb, lin, ms, rays.value
 
+    def shade(self, rays, xi4, medium_xi=None):
+        """closest hit (reference algorithm) + emitted / scatter of that hit with the explicit random numbers xi4 (n x 4)
+        through the device's closed-form samplers. Returns (hits, shade records)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+        n = len(rays)
+        xi4 = np.ascontiguousarray(xi4, dtype=np.float64).reshape(n, 4)
+        mx = np.ascontiguousarray(medium_xi, dtype=np.float64) if medium_xi is not None and self.n_media else None
+        hits = np.zeros(n, dtype=HIT_DTYPE)
+        out = np.zeros(n, dtype=SHADE_DTYPE)
+        rc = self.lib.oracle_shade(self.h, rays.ctypes.data, n, mx.ctypes.data if mx is not None else None, xi4.ctypes.data,
+                                   hits.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle_shade failed")
+        return hits, out
+
+    def logged_rays(self, w, h, spp, cap=2_000_000, reseed=None):
+        """every closest-hit query (primary rays and all bounces) of a w x h x spp render: (n, 7) rays + bounce index"""
+        self.lib.oracle_ray_log_begin.argtypes = [C.c_void_p, C.c_uint64]
+        self.lib.oracle_ray_log_end.restype = C.c_uint64
+        buf = np.zeros((cap, 8))
+        self.lib.oracle_ray_log_begin(buf.ctypes.data, cap)
+        try:
+            self.render(w, h, spp, reseed=reseed)
+        finally:
+            n = self.lib.oracle_ray_log_end()
+        return buf[:n, :7].copy(), (50 - buf[:n, 7]).astype(int)
+
     def close(self):
         if self.h:
             self.lib.oracle_scene_free(self.h)
@@ -89,3 +122,17 @@ class OracleScene:
             self.close()
         except Exception:
             pass
+
+
+def camera_rays(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, time0, time1, st, xi3):
+    """camera::camera + camera::get_ray of the oracle for explicit (s, t) and random numbers (n x 3)"""
+    lib = load()
+    st = np.ascontiguousarray(st, dtype=np.float64).reshape(-1, 2)
+    n = len(st)
+    xi3 = np.ascontiguousarray(xi3, dtype=np.float64).reshape(n, 3)
+    cam9 = np.array(list(lookfrom) + list(lookat) + list(vup), dtype=np.float64)
+    out = np.zeros((n, 7))
+    if lib.oracle_camera_rays(cam9.ctypes.data, vfov, aspect, aperture, focus_dist, time0, time1, st.ctypes.data, xi3.ctypes.data,
+                              n, out.ctypes.data) != 0:
+        raise RuntimeError("oracle_camera_rays failed")
+    return out

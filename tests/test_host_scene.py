@@ -62,9 +62,7 @@ def test_known_structure_numbers(artb):
     assert r["9"]["counts"]["triangle"] == 10200 and r["10"]["counts"]["triangle"] == 5804 and r["11"]["counts"]["triangle"] == 394
 
 
-PRIM = np.dtype([("g", "<f8", 10), ("type", "<u4"), ("material", "<u4"), ("xform", "<u4"), ("dfs_id", "<u4")])
-NODE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("prim_base", "<u4"),
-                 ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])       # FlatNode8, csrc/device/flat_scene.h
+from flat_lib import NODE, PRIM      # noqa: E402  (record layouts of include/artb_flat.h)
 
 
 def node_children(n):
