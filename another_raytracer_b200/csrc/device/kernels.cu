@@ -1213,7 +1213,8 @@ struct Renderer::Impl {
     // wave buffers
     WaveBuffers wb{};
     std::vector<void*> pool_allocs;
-    WaveCounters* counters_host = nullptr;      // pinned
+    WaveCounters* counters_host = nullptr;      // pinned: two snapshots (counters_host[0..1]), polled one batch of waves behind
+    cudaEvent_t poll_ev[2] = { nullptr, nullptr };
     int sm_count = 148;
     size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_extend
     size_t traverse_smem_set[2] = { 0, 0 };     // [kBatch]
@@ -1353,7 +1354,8 @@ void Renderer::init(uint32_t pool_paths)
     w.pairs = dev_alloc<uint2>(impl_->pool_allocs, w.pair_capacity);
     w.region_count = dev_alloc<uint32_t>(impl_->pool_allocs, ARTB_MAX_REGIONS);
     w.c = dev_alloc<WaveCounters>(impl_->pool_allocs, 1);
-    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), sizeof(WaveCounters)));
+    CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&impl_->counters_host), 2 * sizeof(WaveCounters)));
+    for (int k = 0; k < 2; ++k) CUDA_CHECK(cudaEventCreateWithFlags(&impl_->poll_ev[k], cudaEventDisableTiming));
 }
 
 Renderer::~Renderer() { release(); }
@@ -1372,6 +1374,7 @@ void Renderer::release()
     if (impl_->host_count) cudaFree(impl_->host_count);
     if (impl_->host_rgb) cudaFree(impl_->host_rgb);
     if (impl_->counters_host) cudaFreeHost(impl_->counters_host);
+    for (int k = 0; k < 2; ++k) if (impl_->poll_ev[k]) cudaEventDestroy(impl_->poll_ev[k]);
     for (void* p : impl_->batch.bag) cudaFree(p);
     if (impl_->batch.e0) cudaEventDestroy(impl_->batch.e0);
     if (impl_->batch.e1) cudaEventDestroy(impl_->batch.e1);
@@ -1845,9 +1848,14 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
         rp.batch = batch;
         k_round_begin<<<1, 1, 0, st>>>(w.c, n_list_fixed, batch);
         S.launches++;
-        int check_every = 4;
-        while (true) {
-            for (int k = 0; k < check_every; ++k) {
+        // The host looks at the counters ONE BATCH BEHIND: after queueing batch b it copies the counters (as they will be
+        // once b has run) and immediately queues batch b+1, then waits for the copy of batch b. The GPU therefore never
+        // idles while the host wakes up, reads and launches (with several ranks on one box that wake-up is not prompt);
+        // the price is at most one batch of empty waves at the end of a round (a few launches that find nothing to do).
+        int check_every = 4, snap = 0;
+        bool have_prev = false;
+        auto queue_batch = [&](int n_waves) {
+            for (int k = 0; k < n_waves; ++k) {
                 k_shade<<<shade_blocks, 128, 0, st>>>(w, view_, rp, cur);
                 cur ^= 1;
                 if (profile) {
@@ -1874,14 +1882,33 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                 if (profile) { CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used + 4], st)); pairs_used++; }
                 S.waves++;
             }
-            CUDA_CHECK(cudaMemcpyAsync(I.counters_host, w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(cudaMemcpyAsync(&I.counters_host[snap], w.c, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaEventRecord(I.poll_ev[snap], st));
             CUDA_CHECK(cudaGetLastError());
-            const WaveCounters& c = *I.counters_host;
+        };
+        // a snapshot says "done" when every sample of the round was issued and no hit waits to be shaded; `parity` is the
+        // value `cur` had when the snapshot was queued (the shade queues are double-buffered by it)
+        auto done = [&](int which, int parity) {
+            CUDA_CHECK(cudaEventSynchronize(I.poll_ev[which]));
+            const WaveCounters& c = I.counters_host[which];
             uint32_t pending = 0;
-            for (int m = 0; m < MAT_COUNT; ++m) pending += c.n_out[cur][m];
-            if (c.issued >= c.total && pending == 0) break;
-            if (check_every < 32) check_every *= 2;
+            for (int m = 0; m < MAT_COUNT; ++m) pending += c.n_out[parity][m];
+            return c.issued >= c.total && pending == 0;
+        };
+        int prev_parity = 0;
+        while (true) {
+            queue_batch(check_every);
+            const int this_snap = snap, this_parity = cur;
+            snap ^= 1;
+            if (have_prev && done(this_snap ^ 1, prev_parity)) {
+                // the batch just queued runs on an empty pool; wait for it so that the round really is over
+                CUDA_CHECK(cudaEventSynchronize(I.poll_ev[this_snap]));
+                I.counters_host[0] = I.counters_host[this_snap];
+                break;
+            }
+            have_prev = true;
+            prev_parity = this_parity;
+            if (check_every < 8) check_every *= 2;        // polling costs nothing now; a short batch bounds the empty tail
         }
     };
 

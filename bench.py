@@ -51,13 +51,14 @@ WORKLOADS = {
 }
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the closest-hit kernels from the committed ncu --set full capture (profiles/traffic.json,
-    written by tools/ncu_summary.py traffic <report>); None when that file is missing."""
+def ncu_traffic(workload: str):
+    """DRAM bytes per launch of the closest-hit kernels from the committed ncu --set full capture OF THIS WORKLOAD
+    (profiles/traffic.json, one entry per workload, written by tools/ncu_summary.py traffic <report> <workload>); None when no
+    capture of this workload is committed — a capture of another scene is not evidence for this one."""
     p = ROOT / "profiles" / "traffic.json"
     try:
-        t = json.loads(p.read_text())
-        return {"bytes_per_launch": int(sum(v for k, v in t["kernels"].items() if k in ("k_traverse", "k_pairs", "k_finish"))),
+        t = json.loads(p.read_text())[workload]
+        return {"bytes_per_launch": int(sum(v for k, v in t["kernels"].items() if k in ("k_traverse", "k_pairs", "k_finish", "k_walk"))),
                 "per_kernel": t["kernels"], "source": t.get("source")}
     except Exception:
         return None
@@ -164,6 +165,31 @@ def cpu_reference_run(wl: dict, procs: int, spp: int = 1) -> dict:
                 sample=f"{procs} processes of the C++ restatement (oracle/port), {rows} rows of {w}x{h}x{spp}spp each")
 
 
+def cpu_reference_modes(wl: dict) -> list:
+    """the reference's own render modes next to the all-core bound, each ONE process of the
+    unmodified engine (oracle/_ref/ref_engine_*): engine_mode::single (1 thread), parallel_stripes and parallel_images as
+    shipped (hard-wired to 4 worker threads, engine.h:335-445; parallel_images renders spp/4 per worker, so it needs the
+    4-spp binary). Rows whose binary is missing are skipped."""
+    w, h, alias = wl["width"], wl["height"], wl["alias"]
+    rows = []
+    for mode, arg, spp, cores in (("single", "single", 1, 1), ("parallel_stripes", "stripes", 1, 4), ("parallel_images", "images", 4, 4)):
+        exe = ROOT / "oracle" / "_ref" / f"ref_engine_{w}x{h}x{spp}"
+        if not exe.exists():
+            continue
+        with tempfile.TemporaryDirectory() as tmp:
+            env = dict(os.environ, ARTB_ASSETS=str(ROOT / "assets"))
+            try:
+                out = subprocess.run([str(exe), str(alias), arg, os.path.join(tmp, "o.raw")], capture_output=True, text=True, env=env,
+                                     timeout=600).stdout
+                ms = float(json.loads([l for l in out.splitlines() if l.startswith("{")][-1])["elapsed_ms"])
+            except Exception:
+                continue
+        if ms > 0:
+            rows.append({"mode": f"engine_mode::{mode}", "threads": cores, "value": w * h * spp / (ms / 1e3) / 1e6, "unit": "Msamples/s",
+                         "sample": f"one process, {w}x{h}x{spp}spp, engine's own elapsed ms"})
+    return rows
+
+
 def _port_rows(alias, w, h, spp, r0, r1, burn):
     import oracle_lib as O
     s = O.OracleScene(alias)
@@ -239,42 +265,55 @@ def run_cuda_arm(args, wl):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # Everything a step does is queued on ONE stream — the library's (artb_stream): the L2 flush, the render's kernels, the
+    # NCCL reduce of the frames and the accumulation on rank 0 — so a pair of CUDA events on that stream times the whole
+    # step, the exchange included (the reduce used to sit outside the timed value).
+    lib_stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.warmup + args.steps)]
+
     def one_step(k: int) -> dict:
-        flush.zero_()                                                    # L2 flush between timed iterations
-        torch.cuda.synchronize()
-        # partition A (default): every rank renders S samples of every pixel on its own Philox stream and index range;
-        # partition B (--partition tiles, BASELINE configs[4]): every rank renders S samples of its interleaved tiles
-        opt = A.RenderOptions(W, H, S, seed=args.seed, stream=0 if tiles else rank,
-                              sample_begin=(k if tiles else k * world + rank) * S, profile=True,
-                              tile_parts=world if tiles else 1, tile_part=rank if tiles else 0,
-                              mode=1 if args.variance_mask else 0)
-        st = ctx.render_device(cam, opt, step_accum.data_ptr(), step_count.data_ptr() if step_count is not None else None)
-        D.reduce_frames(step_accum)                                      # the one exchange of the path
-        if rank == 0:
-            total_accum.add_(step_accum)
+        with torch.cuda.stream(lib_stream):
+            flush.zero_()                                                # L2 flush between timed iterations
+            e0, e1 = ev[k]
+            e0.record(lib_stream)
+            # partition A (default): every rank renders S samples of every pixel on its own Philox stream and index range;
+            # partition B (--partition tiles, BASELINE configs[4]): every rank renders S samples of its interleaved tiles
+            opt = A.RenderOptions(W, H, S, seed=args.seed, stream=0 if tiles else rank,
+                                  sample_begin=(k if tiles else k * world + rank) * S, profile=True,
+                                  tile_parts=world if tiles else 1, tile_part=rank if tiles else 0,
+                                  mode=1 if args.variance_mask else 0)
+            st = ctx.render_device(cam, opt, step_accum.data_ptr(), step_count.data_ptr() if step_count is not None else None)
+            D.reduce_frames(step_accum)                                  # the one exchange of the path (no-op at N=1)
+            if rank == 0:
+                total_accum.add_(step_accum)
+            e1.record(lib_stream)
         return st
 
     for k in range(args.warmup):
-        one_step(-1 - k if False else k)
+        one_step(k)
+    torch.cuda.synchronize()
     total_accum.zero_()
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.start()                                                      # every rank samples ITS GPU's clocks
     t0 = time.perf_counter()
     stats = [one_step(args.warmup + k) for k in range(args.steps)]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop()
 
-    dev_ms = sum(s["elapsed_ms"] for s in stats)
-    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    render_ms = sum(s["elapsed_ms"] for s in stats)                      # the library's own events: render kernels only
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev[args.warmup:])     # render + reduce + accumulate, per step
+    t = torch.tensor([dev_ms, wall * 1e3, render_ms, -(clocks["sm_mhz"] or 0.0)], dtype=torch.float64, device=dev)
+    tmin = torch.tensor([render_ms], dtype=torch.float64, device=dev)
     agg = torch.tensor([sum(s["samples"] for s in stats), sum(s["rays"] for s in stats), sum(s["launches"] for s in stats)],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    dev_ms_max, wall_ms_max, render_ms_max, min_rank_sm_mhz = float(t[0]), float(t[1]), float(t[2]), -float(t[3])
+    render_ms_min = float(tmin[0])
     samples, rays, launches = (float(x) for x in agg)
 
     # resolve the accumulated image on rank 0 (write_color) and keep a checksum so the work cannot be skipped
@@ -284,34 +323,54 @@ def run_cuda_arm(args, wl):
         torch.cuda.synchronize()
         checksum = int(rgb.to(torch.int64).sum().item())
 
-    # e2e: artb_upload_scene + artb_render with host buffers, every step
+    # e2e: the public API with HOST buffers, every step: scene arrays H2D (artb_upload_scene), render, image D2H.
+    #   N = 1: artb_render (RGB8 + float sums copied back by the library).
+    #   N > 1: every rank uploads and renders its share (artb_render_device), ONE reduce, rank 0 resolves (artb_resolve_device)
+    #          and copies RGB8 + float sums to pinned host memory — the exchange is inside the timed region.
     e2e = None
     if args.e2e_steps > 0:
         e_samples, h2d, d2h = 0, 0, 0
         # one untimed call first: artb_render allocates its device scratch on first use (tens of milliseconds of cudaMalloc)
         ctx.upload(scene)
         ctx.render(cam, A.RenderOptions(W, H, min(S, 8), seed=args.seed, stream=rank, sample_begin=999 * S), want_accum=True)
+        host_rgb = torch.empty((H, W, 3), dtype=torch.uint8, pin_memory=True)
+        host_acc = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
         barrier()
         te = time.perf_counter()
         for k in range(args.e2e_steps):
             ctx.upload(scene)                                            # scene arrays: pageable host -> HBM
             opt = A.RenderOptions(W, H, S, seed=args.seed, stream=rank, sample_begin=(1000 + k * world + rank) * S)
-            img, st, acc, _ = ctx.render(cam, opt, want_accum=True)    # rgb8 + float sums copied back to the host
+            if world == 1:
+                img, st, acc, _ = ctx.render(cam, opt, want_accum=True)    # rgb8 + float sums copied back to the host
+                d2h += st["d2h_bytes"]
+            else:
+                with torch.cuda.stream(lib_stream):
+                    st = ctx.render_device(cam, opt, step_accum.data_ptr(), None)
+                    D.reduce_frames(step_accum)
+                    if rank == 0:
+                        ctx.resolve_device(step_accum.data_ptr(), None, W * H, S * world, rgb.data_ptr())
+                        host_rgb.copy_(rgb, non_blocking=True)
+                        host_acc.copy_(step_accum, non_blocking=True)
+                        d2h += host_rgb.numel() + host_acc.numel() * 4
+                    lib_stream.synchronize()
             e_samples += st["samples"]
             if os.environ.get("ARTB_BENCH_DEBUG"):
                 print(f"e2e step {k}: wall so far {time.perf_counter() - te:.3f} s, device {st['elapsed_ms']:.1f} ms", file=sys.stderr)
             h2d += scene.info["flat_bytes"] + st["h2d_bytes"]
-            d2h += st["d2h_bytes"]
         barrier()
         e_wall = time.perf_counter() - te
         tt = torch.tensor([e_wall], dtype=torch.float64, device=dev)
-        ss = torch.tensor([float(e_samples)], dtype=torch.float64, device=dev)
+        ss = torch.tensor([float(e_samples), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(ss, op=dist.ReduceOp.SUM)
         e2e = {"value": float(ss[0]) / float(tt[0]) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(h2d / args.e2e_steps), "d2h_bytes_per_step": int(d2h / args.e2e_steps),
-               "steps": args.e2e_steps}
+               "h2d_bytes_per_step": int(float(ss[1]) / args.e2e_steps), "d2h_bytes_per_step": int(float(ss[2]) / args.e2e_steps),
+               "steps": args.e2e_steps, "reduce_in_timed_region": world > 1}
+
+    # BASELINE.json configs[4] next to the headline (so that the driver's scaling run carries it): the 1 M-triangle height
+    # field at 4K, tree built on the GPU, TILE-sharded across the ranks, per-pixel variance mask with a 64-spp cap.
+    config5 = run_config5(args, A, D, torch, dist, rank, world, local, dev) if args.config5_steps > 0 else None
 
     if rank == 0:
         ext_ms = sum(s["extend_ms"] for s in stats)
@@ -322,7 +381,7 @@ def run_cuda_arm(args, wl):
         roofline = None
         if b_ray and ext_ms > 0:
             achieved = b_ray * rank0_rays / (ext_ms * 1e-3) / 1e9
-            tr = ncu_traffic()
+            tr = ncu_traffic(args.workload)
             roofline = {"bound": "hbm", "kernel": "closest-hit stage = k_traverse + k_pairs + k_finish (+ k_extend overflow pass)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": tr["bytes_per_launch"] if tr else None,
@@ -339,7 +398,12 @@ def run_cuda_arm(args, wl):
         if world == 1 and not args.no_cpu_baseline:
             c = cpu_reference_run(wl, os.cpu_count() or 1)
             cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            # the reference's own modes beside the all-core bound: single, parallel_stripes and
+            # parallel_images with the 4 threads they ship with
+            cpu["rows"] = cpu_reference_modes(wl) + [{"mode": "all-core: one engine_mode::single process per core", "threads": c["cores"],
+                                                      "value": c["value"], "unit": c["unit"], "sample": c["sample"]}]
         value = samples / (dev_ms_max * 1e-3) / 1e6
+        clocks["min_rank_sm_mhz"] = min_rank_sm_mhz
         line = {
             "metric": "samples_per_sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -350,6 +414,10 @@ def run_cuda_arm(args, wl):
                        "device_bvh_build_ms": bvh_build["build_ms"] if bvh_build["n_nodes"] else None},
             "mrays_per_sec": rays / (dev_ms_max * 1e-3) / 1e6, "rays_per_sample": rays / max(samples, 1),
             "wall_ms_per_step": wall_ms_max / max(args.steps, 1),
+            # the same steps without the exchange: the library's own event time of the render kernels, slowest / fastest rank
+            "render_ms_per_step": {"max_rank": render_ms_max / max(args.steps, 1), "min_rank": render_ms_min / max(args.steps, 1)},
+            "timed_region": "CUDA events on the library stream around render kernels + NCCL reduce + accumulate (L2 flush before, outside)",
+            "config5": config5,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "image_checksum": checksum,
         }
@@ -358,6 +426,55 @@ def run_cuda_arm(args, wl):
         dist.destroy_process_group()
     ctx.close()
     return 0
+
+
+def run_config5(args, A, D, torch, dist, rank, world, local, dev):
+    """One bounded pass of BASELINE.json configs[4]: 3840x2160, 999 698 triangles (alias 12 as one triangle_soup, tree built
+    by the device builder), interleaved 32x32 tiles over the ranks, variance mask capped at 64 spp. Reports whole-job
+    Msamples/s (samples all ranks traced / slowest rank's device time incl. the reduce) and the load balance."""
+    W, H, cap = 3840, 2160, 64
+    scene = A.Scene.build(12, mesh_as_soup=True, device_bvh=True)
+    ctx = A.Context(local, args.pool)
+    ctx.upload(scene)
+    build = ctx.last_bvh_build
+    cam = scene.camera(W, H)
+    accum = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    count = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    out = []
+    for k in range(1 + args.config5_steps):                               # one untimed warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            opt = A.RenderOptions(W, H, cap, seed=args.seed + k, mode=1, tile_size=32, tile_parts=world, tile_part=rank,
+                                  adaptive_min_spp=16, adaptive_batch_spp=16, adaptive_threshold=0.02)
+            st = ctx.render_device(cam, opt, accum.data_ptr(), count.data_ptr())
+            D.reduce_frames(accum, count)
+            e1.record(stream)
+        stream.synchronize()
+        if k:
+            out.append((e0.elapsed_time(e1), st))
+    ms = sum(o[0] for o in out)
+    mine = torch.tensor([ms, float(sum(o[1]["samples"] for o in out)), float(sum(o[1]["rays"] for o in out)),
+                         float(out[-1][1]["pixels_active"] + out[-1][1]["pixels_converged"])], dtype=torch.float64, device=dev)
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allr, mine)
+    else:
+        allr = [mine]
+    ctx.close()
+    scene.close()
+    per = [[float(x) for x in r] for r in allr]
+    ms_max = max(p[0] for p in per)
+    samples = sum(p[1] for p in per)
+    return {"workload": "heightfield_1M_triangles_3840x2160 (BASELINE configs[4])", "partition": f"tiles 32x32 x{world}", "variance_mask": True,
+            "spp_cap": cap, "steps": args.config5_steps, "value": samples / (ms_max * 1e-3) / 1e6, "unit": "Msamples/s",
+            "mrays_per_sec": sum(p[2] for p in per) / (ms_max * 1e-3) / 1e6, "ms_per_step": ms_max / args.config5_steps,
+            "mean_spp": samples / args.config5_steps / (W * H), "device_bvh_build_ms": build["build_ms"], "bvh_nodes": build["n_nodes"],
+            "per_rank": {"ms": [p[0] / args.config5_steps for p in per], "samples": [p[1] / args.config5_steps for p in per],
+                         "pixels": [p[3] for p in per]},
+            "imbalance": {"samples_max_over_mean": max(p[1] for p in per) / (samples / world),
+                          "ms_max_over_mean": ms_max / (sum(p[0] for p in per) / world)}}
 
 
 def main():
@@ -372,6 +489,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config5-steps", type=int, default=2, help="timed steps of the BASELINE configs[4] sub-record (0 = skip)")
     ap.add_argument("--partition", default="samples", choices=["samples", "tiles"])
     ap.add_argument("--variance-mask", action="store_true", help="per-pixel variance mask (adaptive subsampling, north_star 3)")
     args = ap.parse_args()

@@ -75,7 +75,9 @@ def test_gpu_image_psnr_against_converged_oracle(artb, gpu_ctx, path):
     h, w, _ = c["lin"].shape
     scene = artb.Scene.build(alias)
     gpu_ctx.upload(scene)
-    n = 4 * spp                                      # 4x the oracle's samples: the GPU image's own noise is minor
+    # 4x the oracle's samples where that is cheap (the GPU image's own noise is then minor); the 64 Ki-spp fixtures of the
+    # north-star scenes are matched sample for sample (expected: the fixture's limit - 3 dB, still well above 40 dB)
+    n = 4 * spp if spp <= 8192 else spp
     rgb, stats, accum, _ = gpu_ctx.render(scene.camera(w, h), artb.RenderOptions(w, h, n, seed=3), want_accum=True)
     g = accum.astype(np.float64) / n
     halves = psnr8(to8(c["half_a"]), to8(c["half_b"]))
@@ -87,6 +89,10 @@ def test_gpu_image_psnr_against_converged_oracle(artb, gpu_ctx, path):
     assert got >= min(fixture_psnr, 48.0) - 3.0, f"PSNR(G, converged)={got:.2f} dB, fixture noise limit {fixture_psnr:.2f} dB"
     if fixture_psnr >= 43.0:
         assert got >= 40.0
+    if alias in (6, 7, 8):
+        # north_star: "PSNR >= 40 dB against the reference's converged image" on the Next Week final scene / Cornell box
+        assert fixture_psnr >= 45.0, "the committed fixture must itself be converged well beyond 40 dB"
+        assert got >= 40.0, f"north-star bound: PSNR(G, converged reference) = {got:.2f} dB < 40 dB"
 
     def box(x):      # linear-space bias check on 8x8 box-filtered means (separates bias from noise)
         hh, ww = (x.shape[0] // 8) * 8, (x.shape[1] // 8) * 8
@@ -145,6 +151,58 @@ def test_variance_mask_mode_saves_samples_and_stays_close(artb, gpu_ctx):
     mean_fixed = fixed[2].astype(np.float64) / 512
     mean_adapt = acc.astype(np.float64) / np.maximum(cnt, 1)[..., None]
     assert psnr8(to8(mean_adapt), to8(mean_fixed)) > 30.0
+
+
+@pytest.mark.parametrize("alias", [8, 6])
+def test_variance_mask_against_converged_oracle(artb, gpu_ctx, alias):
+    """north_star (3): the per-pixel variance mask compared with the ORACLE's converged image, not with the GPU's own
+    fixed render: at a cap of 16 Ki spp it must reach the quality a fixed render of the same total sample count reaches
+    (within 1.5 dB), stay above 38 dB, and spend fewer samples than the cap."""
+    c = np.load(GOLDEN / f"converged_{alias}_128x128.npz")
+    h, w, _ = c["lin"].shape
+    scene = artb.Scene.build(alias)
+    gpu_ctx.upload(scene)
+    cam = scene.camera(w, h)
+    cap = 16384
+    _, st, acc, cnt = gpu_ctx.render(cam, artb.RenderOptions(w, h, cap, seed=5, mode=1, adaptive_min_spp=256, adaptive_batch_spp=256,
+                                                             adaptive_threshold=0.004), want_accum=True, want_count=True)
+    adaptive = acc.astype(np.float64) / np.maximum(cnt, 1)[..., None]
+    mean_spp = st["samples"] / (w * h)
+    fixed_spp = max(int(mean_spp), 1)
+    _, _, facc, _ = gpu_ctx.render(cam, artb.RenderOptions(w, h, fixed_spp, seed=6), want_accum=True)
+    fixed = facc.astype(np.float64) / fixed_spp
+    ref8 = to8(c["lin"])
+    p_adaptive, p_fixed = psnr8(to8(adaptive), ref8), psnr8(to8(fixed), ref8)
+    print(f"alias {alias}: variance mask {mean_spp:.0f} spp/pixel (cap {cap}) PSNR {p_adaptive:.2f} dB; fixed {fixed_spp} spp PSNR {p_fixed:.2f} dB")
+    assert cnt.min() >= 256 and cnt.max() <= cap and st["samples"] == int(cnt.sum())
+    assert mean_spp < 0.9 * cap, "the mask must retire converged pixels"
+    assert p_adaptive >= 38.0
+    assert p_adaptive >= p_fixed - 1.5
+
+
+def test_fixed_mode_counts_and_device_tile_lists(artb, gpu_ctx):
+    """artb_render's count buffer in ARTB_MODE_FIXED (include/artb.h: samples per pixel) and the tile lists built on the
+    device: odd image sizes, three parts, edge tiles narrower than the tile size"""
+    from another_raytracer_b200 import distributed as D
+    scene = artb.Scene.build(6)
+    gpu_ctx.upload(scene)
+    w, h, spp = 100, 70, 8
+    cam = scene.camera(w, h)
+    _, st, full, cnt = gpu_ctx.render(cam, artb.RenderOptions(w, h, spp, seed=4), want_accum=True, want_count=True)
+    assert np.all(cnt == spp) and st["samples"] == w * h * spp
+    total = np.zeros_like(full)
+    covered = np.zeros((h, w), dtype=int)
+    for parts, ts in ((3, 32), (2, 16), (5, 7)):
+        total[:] = 0; covered[:] = 0
+        for part in range(parts):
+            _, st, acc, c = gpu_ctx.render(cam, artb.RenderOptions(w, h, spp, seed=4, tile_size=ts, tile_parts=parts, tile_part=part),
+                                           want_accum=True, want_count=True)
+            mask = D.owned_pixel_mask(w, h, ts, D.tile_share(ts, part, parts))
+            assert np.array_equal(c, np.where(mask, spp, 0)), f"parts={parts} ts={ts} part={part}"
+            assert np.all(acc[~mask] == 0) and st["samples"] == int(mask.sum()) * spp
+            total += acc; covered += mask
+        assert np.all(covered == 1)
+        assert np.allclose(total, full, rtol=1e-4, atol=1e-4)
 
 
 def test_engine_mirror_run_contract(artb, gpu_ctx, capsys):

@@ -3,7 +3,7 @@
 # and prints samples/s, extend ms per launch, extend share, image checksum. Experiment helper for gpurun calls.
 for lib in another_raytracer_b200/libartb*.so; do
   printf "%-45s " "$lib"
-  ARTB_LIB=$PWD/$lib python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 "$@" 2>&1 | tail -1 | python -c "
+  ARTB_LIB=$PWD/$lib python bench.py --steps 2 --warmup 1 --no-cpu-baseline --e2e-steps 0 --config5-steps 0 "$@" 2>&1 | tail -1 | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
