@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libartb.so"
 
 # every symbol include/artb.h declares (tests/test_abi_symbols.py checks the header against this list)
 SYMBOLS = [
-    "artb_abi_version", "artb_create", "artb_destroy", "artb_last_error",
+    "artb_abi_version", "artb_device_count", "artb_create", "artb_context_devices", "artb_destroy", "artb_last_error",
     "artb_scene_build", "artb_scene_from_graph", "artb_scene_free", "artb_scene_get_info", "artb_scene_dump_graph", "artb_scene_get_flat",
     "artb_upload_scene", "artb_upload_flat",
     "artb_trace_batch", "artb_trace_batch_device", "artb_trace_overflow_rays",
@@ -30,8 +30,13 @@ ARTB_E_INVALID, ARTB_E_NO_DEVICE, ARTB_E_CUDA, ARTB_E_SCENE, ARTB_E_EMPTY_SCENE,
 MODE_FIXED, MODE_VARIANCE_MASK, MODE_ADAPTIVE_SQUARES = 0, 1, 2
 
 
+MAX_DEVICES = 8
+PARTITION_SAMPLES, PARTITION_TILES = 0, 1
+
+
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("pool_paths", C.c_uint32)]
+    _fields_ = [("device", C.c_int32), ("pool_paths", C.c_uint32), ("n_devices", C.c_int32), ("partition", C.c_int32),
+                ("devices", C.c_int32 * MAX_DEVICES)]
 
 
 class SceneOptions(C.Structure):
@@ -103,7 +108,8 @@ class Stats(C.Structure):
                 ("launches", C.c_uint64), ("extend_ms", C.c_double), ("extend_launches", C.c_uint64),
                 ("pixels_active", C.c_uint64), ("pixels_converged", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("traverse_ms", C.c_double), ("pairs_ms", C.c_double), ("finish_ms", C.c_double),
-                ("overflow_rays", C.c_uint64)]
+                ("overflow_rays", C.c_uint64), ("n_devices", C.c_int32), ("reserved", C.c_int32), ("reduce_ms", C.c_double),
+                ("device_ms", C.c_double * MAX_DEVICES), ("device_samples", C.c_uint64 * MAX_DEVICES)]
 
 
 _lib = None
@@ -121,6 +127,9 @@ def load() -> C.CDLL:
     lib = C.CDLL(path)
     vp, dp = C.c_void_p, C.POINTER(C.c_double)
     lib.artb_abi_version.restype = C.c_int
+    lib.artb_device_count.restype = C.c_int
+    lib.artb_context_devices.argtypes = [vp]
+    lib.artb_context_devices.restype = C.c_int
     lib.artb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     lib.artb_destroy.argtypes = [vp]
     lib.artb_destroy.restype = None
@@ -163,7 +172,7 @@ def load() -> C.CDLL:
                  "artb_upload_flat", "artb_trace_batch", "artb_trace_batch_device", "artb_render", "artb_render_device",
                  "artb_resolve_device", "artb_save_png"):
         getattr(lib, name).restype = C.c_int
-    if lib.artb_abi_version() != 1:
+    if lib.artb_abi_version() != 2:
         raise ImportError("libartb.so ABI version mismatch")
     _lib = lib
     return lib

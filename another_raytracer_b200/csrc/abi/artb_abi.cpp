@@ -16,6 +16,9 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
+
+#include <cuda_runtime_api.h>
 
 using namespace artb;
 
@@ -27,7 +30,9 @@ struct artb_scene {
 };
 
 struct artb_ctx {
-    std::unique_ptr<Renderer> renderer;
+    std::unique_ptr<Renderer> renderer;                       // devices[0]: every call but artb_upload_* / artb_render uses only this one
+    std::vector<std::unique_ptr<Renderer>> peers;             // devices[1..] of a multi-device context
+    int partition = ARTB_PARTITION_SAMPLES;
     std::string last_error;
     uint64_t last_upload_bytes = 0;
 };
@@ -138,7 +143,13 @@ int artb_create(const artb_config* cfg, artb_ctx** out)
     *out = nullptr;
     try {
         auto ctx = std::make_unique<artb_ctx>();
-        ctx->renderer = std::make_unique<Renderer>(cfg ? cfg->device : 0, cfg ? cfg->pool_paths : 0);
+        const int n = cfg ? cfg->n_devices : 0;
+        if (n < 0 || n > ARTB_MAX_DEVICES) return fail(nullptr, ARTB_E_INVALID, "n_devices out of range");
+        if (cfg && cfg->partition != ARTB_PARTITION_SAMPLES && cfg->partition != ARTB_PARTITION_TILES)
+            return fail(nullptr, ARTB_E_INVALID, "unknown partition");
+        ctx->renderer = std::make_unique<Renderer>(cfg ? (n >= 1 ? cfg->devices[0] : cfg->device) : 0, cfg ? cfg->pool_paths : 0);
+        for (int k = 1; k < n; ++k) ctx->peers.push_back(std::make_unique<Renderer>(cfg->devices[k], cfg->pool_paths));
+        if (cfg) ctx->partition = cfg->partition;
         *out = ctx.release();
         return ARTB_OK;
     } catch (const std::exception& e) {
@@ -149,6 +160,15 @@ int artb_create(const artb_config* cfg, artb_ctx** out)
 }
 
 void artb_destroy(artb_ctx* ctx) { delete ctx; }
+
+int artb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int artb_context_devices(const artb_ctx* ctx) { return ctx ? 1 + int(ctx->peers.size()) : 0; }
 
 const char* artb_last_error(const artb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
 
@@ -264,7 +284,8 @@ int artb_upload_scene(artb_ctx* ctx, const artb_scene* s)
     if (s->host.objects.objects.empty()) return fail(ctx, ARTB_E_EMPTY_SCENE, "Invalid input scene!");
     return guarded(ctx, [&]() -> int {
         ctx->renderer->upload(s->flat);
-        ctx->last_upload_bytes = ctx->renderer->scene_bytes();
+        for (auto& r : ctx->peers) r->upload(s->flat);
+        ctx->last_upload_bytes = ctx->renderer->scene_bytes() * (1 + ctx->peers.size());
         return ARTB_OK;
     });
 }
@@ -395,7 +416,8 @@ int artb_upload_flat(artb_ctx* ctx, const artb_flat_scene* f)
                 if (uint32_t(pn.perm_x[i]) > 255u || uint32_t(pn.perm_y[i]) > 255u || uint32_t(pn.perm_z[i]) > 255u)
                     throw std::logic_error("flat scene: Perlin permutation entry out of range");
         ctx->renderer->upload(fs);
-        ctx->last_upload_bytes = ctx->renderer->scene_bytes();
+        for (auto& r : ctx->peers) r->upload(fs);
+        ctx->last_upload_bytes = ctx->renderer->scene_bytes() * (1 + ctx->peers.size());
         return ARTB_OK;
     });
 }
@@ -484,9 +506,24 @@ int artb_render(artb_ctx* ctx, const artb_camera* cam, const artb_render_params*
         return fail(ctx, ARTB_E_ADAPTIVE_SIZE, "for adaptive strategy image size should perfectly fit big square size for now!!");
     return guarded(ctx, [&]() -> int {
         RenderStats s;
-        ctx->renderer->render_host(make_camera(*cam), to_params(*p), rgb8_out, accum_out, count_out, &s);
+        const size_t n_dev = 1 + ctx->peers.size();
+        std::vector<RenderStats> per(n_dev);
+        double reduce_ms = 0;
+        if (n_dev > 1 && p->mode != ARTB_MODE_ADAPTIVE_SQUARES) {
+            std::vector<Renderer*> peers;
+            for (auto& r : ctx->peers) peers.push_back(r.get());
+            ctx->renderer->render_host_multi(peers.data(), int(peers.size()), ctx->partition, make_camera(*cam), to_params(*p), rgb8_out,
+                                             accum_out, count_out, &s, per.data(), &reduce_ms);
+        } else {
+            // one device, and the reference's own adaptive strategy (a serial refinement of squares): devices[0]
+            ctx->renderer->render_host(make_camera(*cam), to_params(*p), rgb8_out, accum_out, count_out, &s);
+            per[0] = s;
+        }
         to_stats(s, stats);
         if (stats) {
+            stats->n_devices = int32_t(n_dev);
+            stats->reduce_ms = reduce_ms;
+            for (size_t k = 0; k < n_dev && k < ARTB_MAX_DEVICES; ++k) { stats->device_ms[k] = per[k].elapsed_ms; stats->device_samples[k] = per[k].samples; }
             const uint64_t px = uint64_t(p->width) * uint64_t(p->height);
             stats->h2d_bytes = sizeof(CameraParams) + sizeof(RenderParams);
             stats->d2h_bytes = px * 3 + (accum_out ? px * 12 : 0) + (count_out ? px * 4 : 0);

@@ -26,6 +26,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace artb {
@@ -372,6 +374,62 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
     }
 }
 
+// The same merge with its compare-and-swap left IN FLIGHT: issue_merge decides from the peeked copy whether the candidate
+// can win at all, and if so fires the 128-bit CAS without looking at what it returns; resolve_merge — called one loop
+// iteration later, after the next pair's loads have been issued — reads the result. Only a CAS that lost a race (another
+// pair of the same ray got in between) or an exact tie takes the loop of merge_hit. The round trip of the atomic (15 % of
+// this kernel's stall samples when it was waited for in place) now overlaps the next pair's gathers.
+struct PendingMerge {
+    unsigned long long exp_lo, exp_hi, old_lo, old_hi;
+    double t;
+    uint32_t ray, prim, dfs, other;
+    bool active;
+};
+
+__device__ __forceinline__ void issue_merge(const TraceIO& io, PendingMerge& pm, uint32_t ray_id, unsigned long long cur_lo,
+                                            unsigned long long cur_hi, double t, uint32_t prim, uint32_t dfs)
+{
+    pm.active = false;
+    unsigned long long new_lo = (unsigned long long)__double_as_longlong(t);
+    unsigned long long new_hi = (unsigned long long)prim | ((unsigned long long)dfs << 32);
+    const double cur_t = __longlong_as_double((long long)cur_lo);
+    const int32_t cur_prim = int32_t(uint32_t(cur_hi));
+    if (cur_prim == ARTB_HIT_OVERFLOW) return;
+    uint32_t other = 0xffffffffu;
+    if (cur_prim >= 0) {
+        if (t > cur_t) return;
+        if (t == cur_t) {
+            const uint32_t cur_dfs = uint32_t(cur_hi >> 32);
+            if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
+            else other = uint32_t(cur_prim);
+            new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
+        }
+    } else if (!(t <= cur_t)) return;
+    pm.exp_lo = cur_lo; pm.exp_hi = cur_hi;
+    pm.t = t; pm.ray = ray_id; pm.prim = prim; pm.dfs = dfs; pm.other = other;
+    pm.active = true;
+    PathHit* h = io.hits.at(ray_id);
+    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
+                 "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
+                 : "=l"(pm.old_lo), "=l"(pm.old_hi) : "l"(cur_lo), "l"(cur_hi), "l"(new_lo), "l"(new_hi), "l"(h) : "memory");
+}
+
+template <bool kBatch>
+__device__ __forceinline__ void resolve_merge(const TraceIO& io, PendingMerge& pm)
+{
+    if (!pm.active) return;
+    pm.active = false;
+    if (pm.old_lo == pm.exp_lo && pm.old_hi == pm.exp_hi) {
+        if (pm.other != 0xffffffffu) {
+            PathTie* tie = io.ties.at(pm.ray);
+            const uint32_t k = atomicAdd(&tie->n, 1u);
+            if (k < 3u) tie->prim[k] = pm.other;
+        }
+        return;
+    }
+    merge_hit<kBatch>(io, pm.ray, pm.old_lo, pm.old_hi, pm.t, pm.prim, pm.dfs);     // lost a race: start over from the fresh value
+}
+
 #ifndef ARTB_TRAVERSE_THREADS
 #define ARTB_TRAVERSE_THREADS 1024
 #endif
@@ -390,13 +448,37 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
 extern __shared__ uint4 smem_nodes[];
 struct WarpFeed { float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };      // 1 KB per warp
 
+// The traversal stack of k_traverse. The collector pushes at most one entry per level of 8-wide nodes, and the trees of
+// the reference's scenes are 2-8 levels deep, so the stack fits in SHARED memory next to the node array ([entry][thread]:
+// a warp's accesses to one entry are 32 consecutive words pairs, no bank conflicts). As a lane-private array it lived in
+// local memory: an LDL / STL round trip through L1 on every pop and push, 7 % of the kernel's stall samples.
+#ifndef ARTB_SMEM_STACK
+#define ARTB_SMEM_STACK 8             // entries; trees deeper than this use the local-memory stack
+#endif
+template <int kEntries>
+struct TraverseStack {
+    uint2 local[kEntries ? 1 : ARTB_STACK_DEPTH];
+    uint2* shared;
+    __device__ __forceinline__ uint2& operator[](int i)
+    {
+        if (kEntries) return shared[uint32_t(i) * ARTB_TRAVERSE_THREADS];
+        return local[i];
+    }
+    __device__ __forceinline__ const uint2& operator[](int i) const
+    {
+        if (kEntries) return shared[uint32_t(i) * ARTB_TRAVERSE_THREADS];
+        return local[i];
+    }
+};
+
 // kShared: every block first stages the whole 8-wide node array (a few hundred 80-byte nodes for the reference's
 // scenes) in shared memory with 16-byte loads and traverses it there; one block per SM, so one copy per SM.
 // Otherwise nodes are read through L1/L2.
-template <bool kShared, bool kBatch>
+template <bool kShared, bool kBatch, int kSmemStack>
 __global__ void __launch_bounds__(kShared ? ARTB_TRAVERSE_THREADS : 256, kShared ? ARTB_TRAVERSE_BLOCKS : 3)
 k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
+    static_assert(!kSmemStack || kShared, "the shared-memory stack comes with the shared-memory node array");
     __shared__ uint32_t s_pairs;      // pairs this block has appended to its region
     __shared__ WarpFeed feeds[(kShared ? ARTB_TRAVERSE_THREADS : 256) / 32];
     const uint32_t n = *io.n_ptr;
@@ -414,10 +496,13 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     }
     if (threadIdx.x == 0) s_pairs = 0;
     const FlatNode8* nodes = s.nodes;
+    TraverseStack<kSmemStack> stack;
+    stack.shared = nullptr;
     if (kShared) {
         const uint4* src = reinterpret_cast<const uint4*>(s.nodes);
         for (uint32_t i = threadIdx.x; i < s.n_nodes * 5u; i += blockDim.x) smem_nodes[i] = __ldg(src + i);
         nodes = reinterpret_cast<const FlatNode8*>(smem_nodes);
+        if (kSmemStack) stack.shared = reinterpret_cast<uint2*>(smem_nodes + (s.n_nodes ? s.n_nodes * 5u : 1u)) + threadIdx.x;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -426,7 +511,6 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     const float t_min_f = d2f_rd(io.t_min), t_max_f = d2f_ru(io.t_max);
     const uint32_t cap = io.pb.region_cap;
     uint2* region = io.pb.pairs + size_t(blockIdx.x) * cap;
-    uint2 stack[ARTB_STACK_DEPTH];
     BoxRay br;
     Collector col;
     uint32_t id = 0;
@@ -439,17 +523,31 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     // handful of shared loads, so lanes are refilled one by one, at once, while their neighbours keep walking.
     WarpFeed& feed = feeds[threadIdx.x >> 5];
     uint32_t feed_count = 0;          // warp-uniform: entries not handed out yet (taken from the top)
+    // The chunk of 32 rays the warp converts at its NEXT refill is claimed one refill ahead and its records are
+    // prefetched, so that the refill — at which all 32 lanes wait — finds them in L1/L2 instead of in DRAM (12 % of
+    // this kernel's stall samples sat on those loads).
+    uint32_t ahead_base = 0, ahead_rid = 0;
+    auto claim_ahead = [&]() {
+        if (lane == 0) ahead_base = atomicAdd(io.cursor_traverse, 32u);
+        ahead_base = __shfl_sync(0xffffffffu, ahead_base, 0);
+        if (ahead_base + uint32_t(lane) < n) {
+            ahead_rid = io.list ? io.list[ahead_base + uint32_t(lane)] : ahead_base + uint32_t(lane);
+            if (kBatch) prefetch_l1(io.batch_rays + size_t(ahead_rid) * 7);
+            else prefetch_l1(io.rays.at(ahead_rid));
+        }
+    };
+    claim_ahead();
     for (;;) {
         uint32_t m_active = __ballot_sync(0xffffffffu, active);
         if (m_active != 0xffffffffu) {
             if (feed_count == 0u && more) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(io.cursor_traverse, 32u);
-                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t base = ahead_base;
                 const uint32_t got = base < n ? (n - base < 32u ? n - base : 32u) : 0u;
+                const uint32_t my_rid = ahead_rid;
+                if (base + 32u >= n) more = false;
+                else claim_ahead();             // the chunk after this one: id loads + prefetches fly while this one is converted
                 if (uint32_t(lane) < got) {
-                    const uint32_t idx = base + uint32_t(lane);
-                    const uint32_t rid = io.list ? io.list[idx] : idx;
+                    const uint32_t rid = my_rid;
                     const BoxRay b = make_box_ray(make_trav_ray(trace_io_ray<kBatch>(io, rid)));
                     feed.inv[0][lane] = b.inv[0]; feed.inv[1][lane] = b.inv[1]; feed.inv[2][lane] = b.inv[2];
                     feed.c[0][lane] = b.c[0]; feed.c[1][lane] = b.c[1]; feed.c[2][lane] = b.c[2];
@@ -460,7 +558,6 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
                 }
                 __syncwarp();
                 feed_count = got;
-                if (base + 32u >= n) more = false;
             }
             if (feed_count) {
                 const uint32_t idle = ~m_active;
@@ -493,7 +590,8 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
             active = false;
         }
         warp_sync();
-        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, tn_min, s.one_bits, nullptr);
+        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, tn_min, s.one_bits, nullptr,
+                                 kSmemStack ? kSmemStack : ARTB_STACK_DEPTH);
         warp_sync();
         // append this step's pairs
         const uint32_t cnt = uint32_t(__popc(prim_mask));
@@ -639,7 +737,15 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
 #ifndef ARTB_PAIRS_PREFETCH
 #define ARTB_PAIRS_PREFETCH 0           // measured: prefetching ray / primitive lines during the sort costs 10 % (L1 thrash)
 #endif
+#ifndef ARTB_PAIRS_PER_THREAD
 #define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory
+#endif
+#ifndef ARTB_PAIRS_DEFER
+#define ARTB_PAIRS_DEFER 1            // the 128-bit CAS of a merge is checked one iteration later (PendingMerge)
+#endif
+#ifndef ARTB_PAIRS_L2_AHEAD
+#define ARTB_PAIRS_L2_AHEAD 1         // records of the block's next tile are prefetched into L2 while this tile is processed
+#endif
 template <bool kBatch>
 __global__ void __launch_bounds__(ARTB_PAIRS_THREADS, ARTB_PAIRS_BLOCKS)
 k_pairs(TraceIO io, SceneView s)
@@ -670,11 +776,29 @@ k_pairs(TraceIO io, SceneView s)
         // cannot win and nothing is loaded or tested for it. The record loads also warm the rays' lines; all of a
         // thread's loads are issued before the first one is looked at.
         unsigned long long rec_lo[ARTB_PAIRS_PER_THREAD], rec_hi[ARTB_PAIRS_PER_THREAD];
+#if ARTB_PAIRS_L2_AHEAD
+        // the block's NEXT tile: its pairs are read now (coalesced, cheap) only to start pulling their rays' records from
+        // DRAM into L2 — by the time that tile is processed its first touches are L2 hits instead of DRAM round trips
+        uint2 ahead[ARTB_PAIRS_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
+            const uint32_t i = t0 + J * kTile + uint32_t(k) * ARTB_PAIRS_THREADS + threadIdx.x;
+            ahead[k] = i < cnt ? region[i] : make_uint2(0xffffffffu, 0u);
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             rec_lo[k] = 0; rec_hi[k] = 0;
             if (pr[k].x != 0xffffffffu) peek_hit(io.hits.at(pr[k].x & 0xffffffu), rec_lo[k], rec_hi[k]);
         }
+#if ARTB_PAIRS_L2_AHEAD
+#pragma unroll
+        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k)
+            if (ahead[k].x != 0xffffffffu) {
+                prefetch_l2(io.hits.at(ahead[k].x & 0xffffffu));
+                if (!kBatch) prefetch_l2(io.rays.at(ahead[k].x & 0xffffffu));
+            }
+#endif
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             uint32_t cls = ARTB_PRIM_CLASSES;
@@ -704,6 +828,11 @@ k_pairs(TraceIO io, SceneView s)
         const uint32_t n_live = class_start[ARTB_PRIM_CLASSES];
         // 3. one pair per thread, warps (almost) uniform in class. Warp-uniform trip count and explicit re-convergence
         // points: the primitive tests have many exits, and without them the compiler clones the merge into every exit.
+#if ARTB_PAIRS_DEFER
+        PendingMerge pm;
+        pm.active = false;
+        pm.exp_lo = pm.exp_hi = pm.old_lo = pm.old_hi = 0; pm.t = 0; pm.ray = pm.prim = pm.dfs = pm.other = 0;
+#endif
         for (uint32_t base = threadIdx.x & ~31u; base < n_live; base += ARTB_PAIRS_THREADS) {
             const uint32_t i = base + (threadIdx.x & 31u);
             bool ok = false;
@@ -718,13 +847,24 @@ k_pairs(TraceIO io, SceneView s)
                 const FlatPrim& p = s.prims[prim];
                 dfs = p.dfs_id;
                 DRay q = trace_io_ray<kBatch>(io, ray);
+#if ARTB_PAIRS_DEFER
+                resolve_merge<kBatch>(io, pm);       // the previous pair's CAS: its round trip ran under the loads above
+#endif
                 if (p.xform) q = to_object_space(s, p.xform, q);
                 ok = surface_t(p, q, io.t_min, io.t_max, t);
             }
             warp_sync();
+#if ARTB_PAIRS_DEFER
+            resolve_merge<kBatch>(io, pm);           // (lanes that had no pair this iteration)
+            if (ok && t == t) issue_merge(io, pm, ray, cur_lo, cur_hi, t, prim, dfs);
+#else
             if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs);
+#endif
             warp_sync();
         }
+#if ARTB_PAIRS_DEFER
+        resolve_merge<kBatch>(io, pm);
+#endif
         __syncthreads();
     }
 }
@@ -765,32 +905,36 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     const uint32_t stride = gridDim.x * blockDim.x;
     // The ray id of the NEXT iteration is loaded one iteration ahead and its records are prefetched while this
     // iteration computes; all records of this iteration are requested together, before anything waits on them.
+    // (two iterations deep: the id of iteration k+2 is loaded while the records of iteration k+1, whose id arrived one
+    // iteration ago, are prefetched — the prefetch no longer waits for the id it has just asked for)
     uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
-    uint32_t id = 0;
+    uint32_t id = 0, next_id = 0;
     if (base + uint32_t(lane) < n) id = io.list ? io.list[base + lane] : base + uint32_t(lane);
+    if (base + stride + uint32_t(lane) < n) next_id = io.list ? io.list[base + stride + lane] : base + stride + uint32_t(lane);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
         const uint32_t next_idx = idx + stride;
-        uint32_t next_id = 0;
-        if (next_idx < n) next_id = io.list ? io.list[next_idx] : next_idx;
+        const uint32_t far_idx = next_idx + stride;
+        uint32_t far_id = 0;
+        if (far_idx < n) far_id = io.list ? io.list[far_idx] : far_idx;
         PathHit ph;
         ph.t = 0; ph.prim = -1; ph.dfs = 0;
         DRay r;
         r.o = mk3(0, 0, 0); r.d = mk3(1, 0, 0); r.tm = 0;
         PathAux a;
         a.thr[0] = a.thr[1] = a.thr[2] = 0.f; a.pixel = a.sample = a.rng_block = a.depth = a.pad = 0;
-        if (valid) {
-            ph = load_hit(io.hits.at(id));
-            r = trace_io_ray<kBatch>(io, id);
-            if (!kBatch) load_aux(io.aux.at(id), a);
-        }
         if (next_idx < n) {
             prefetch_l1(io.hits.at(next_id));
             if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
             else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
+        }
+        if (valid) {
+            ph = load_hit(io.hits.at(id));
+            r = trace_io_ray<kBatch>(io, id);
+            if (!kBatch) load_aux(io.aux.at(id), a);
         }
         // flagged by k_traverse (pairs did not fit), or more leaves tied than the list holds: the one-phase pass traces the ray
         const bool tied = valid && ph.prim >= 0 && (ph.dfs & ARTB_HIT_TIED) != 0u;
@@ -854,6 +998,7 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 #endif
         }
         id = next_id;
+        next_id = far_id;
     }
     if (!kBatch) append_commit(pend);
 }
@@ -953,16 +1098,27 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
         if (!valid) return 0u;
         return m == Q_REGEN ? w.q_regen[cur][i] : w.q_shade[size_t(m) * w.pool + i];
     };
-    // software pipeline: the slot of the NEXT iteration is loaded one iteration ahead and its records are prefetched
-    // while this iteration shades
+    // software pipeline, two iterations deep: the slot id of iteration k+2 is loaded while iteration k shades, and the
+    // records of iteration k+1 — whose id arrived during iteration k-1 — are prefetched at the same time. (One stage
+    // deep, the prefetch had to wait for the id it had just asked for: 20 % of this kernel's stall samples.)
+#ifndef ARTB_SHADE_PIPE
+#define ARTB_SHADE_PIPE 2
+#endif
     uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int m = 0; uint32_t i = 0; bool valid = false;
     uint32_t slot = locate(wi, m, i, valid);
+    int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
+    uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
-        int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
-        const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
+#if ARTB_SHADE_PIPE >= 2
+        int far_m = 0; uint32_t far_i = 0; bool far_valid = false;
+        const uint32_t far_slot = locate(wi + 2u * n_warps, far_m, far_i, far_valid);
+        if (next_valid && next_m != Q_REGEN) {
+            prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
+        }
+#endif
         int key = -1;                       // 0: a ray for the next wave, 1: slot is free
         if (m == Q_REGEN) {
             if (valid) {
@@ -993,9 +1149,11 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
             PathAux a;
             load_aux(w.aux.at(slot), a);
             const PathHit ph = load_hit(w.hits.at(slot));
+#if ARTB_SHADE_PIPE < 2
             if (next_valid && next_m != Q_REGEN) {
                 prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
             }
+#endif
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
             key = 1;
@@ -1022,6 +1180,11 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
         append_reserve(pend, key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1],
                        key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1], slot, lane);
         m = next_m; i = next_i; valid = next_valid; slot = next_slot;
+#if ARTB_SHADE_PIPE >= 2
+        next_m = far_m; next_i = far_i; next_valid = far_valid; next_slot = far_slot;
+#else
+        next_slot = locate(wi + 2u * n_warps, next_m, next_i, next_valid);
+#endif
     }
     append_commit(pend);
 }
@@ -1216,8 +1379,9 @@ struct Renderer::Impl {
     WaveCounters* counters_host = nullptr;      // pinned: two snapshots (counters_host[0..1]), polled one batch of waves behind
     cudaEvent_t poll_ev[2] = { nullptr, nullptr };
     int sm_count = 148;
-    size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_extend
-    size_t traverse_smem_set[2] = { 0, 0 };     // [kBatch]
+    size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_traverse
+    size_t max_traverse_smem = 112 << 10;       // dynamic shared memory k_traverse may ask for (nodes + traversal stack)
+    int bvh_depth = ARTB_STACK_DEPTH;           // levels of 8-wide nodes of the uploaded tree (upload / build_bvh_device)
     // device scratch of render_host (grow-only: cudaMalloc costs tens of milliseconds next to a render)
     float* host_accum = nullptr; uint32_t* host_count = nullptr; uint8_t* host_rgb = nullptr;
     size_t host_pixels = 0;
@@ -1269,14 +1433,15 @@ struct Renderer::Impl {
             return;
         }
         const size_t node_bytes = std::max<size_t>(size_t(view.n_nodes) * sizeof(FlatNode8), 16);
-        if (nodes_fit_shared(view)) {
-            if (node_bytes > traverse_smem_set[kBatch]) {
-                CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(node_bytes)));
-                traverse_smem_set[kBatch] = node_bytes;
-            }
-            k_traverse<true, kBatch><<<io.pb.n_regions, ARTB_TRAVERSE_THREADS, node_bytes, st>>>(io, view, w.c, cur);
+        const size_t stack_bytes = size_t(ARTB_SMEM_STACK) * ARTB_TRAVERSE_THREADS * sizeof(uint2);
+        if (nodes_fit_shared(view) && ARTB_SMEM_STACK > 0 && bvh_depth <= ARTB_SMEM_STACK && node_bytes + stack_bytes <= max_traverse_smem) {
+            k_traverse<true, kBatch, ARTB_SMEM_STACK><<<io.pb.n_regions, ARTB_TRAVERSE_THREADS, node_bytes + stack_bytes, st>>>(io, view, w.c, cur);
+        } else if (nodes_fit_shared(view)) {
+            // (the opt-in shared-memory limit of k_traverse is raised once, in Renderer::init: the attribute belongs to the
+            // function, not to this object — a per-object cache let a second context with a smaller tree LOWER it)
+            k_traverse<true, kBatch, 0><<<io.pb.n_regions, ARTB_TRAVERSE_THREADS, node_bytes, st>>>(io, view, w.c, cur);
         } else {
-            k_traverse<false, kBatch><<<io.pb.n_regions, 256, 0, st>>>(io, view, w.c, cur);
+            k_traverse<false, kBatch, 0><<<io.pb.n_regions, 256, 0, st>>>(io, view, w.c, cur);
         }
         if (ev) CUDA_CHECK(cudaEventRecord(ev[0], st));
         const uint32_t J = std::max(1u, uint32_t(sm_count) * ARTB_PAIRS_BLOCKS / io.pb.n_regions);
@@ -1329,6 +1494,16 @@ void Renderer::init(uint32_t pool_paths)
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     impl_->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("ARTB_MAX_SHARED_NODES")) impl_->max_shared_nodes = size_t(atoll(e));   // tuning knob (bytes)
+    impl_->max_shared_nodes = std::min<size_t>(impl_->max_shared_nodes, size_t(prop.sharedMemPerBlockOptin) - (48u << 10));
+    // the tree walk stages up to max_shared_nodes bytes of nodes in dynamic shared memory: permit that once per device
+    // static shared memory of the kernel: the warp feeds (1 KB per warp) + a few words
+    impl_->max_traverse_smem = size_t(prop.sharedMemPerBlockOptin) - (ARTB_TRAVERSE_THREADS / 32) * sizeof(WarpFeed) - 1024;
+    CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_shared_nodes)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_shared_nodes)));
+#if ARTB_SMEM_STACK > 0
+    CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, false, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, true, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
+#endif
     if (const char* e = getenv("ARTB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoll(e)));
     cudaStream_t st;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1437,6 +1612,7 @@ void Renderer::upload(const FlatScene& fs)
     view_ = v;
     scene_bytes_ = bytes;
     has_scene_ = true;
+    impl_->bvh_depth = fs.bvh_depth;
     max_dfs_id_ = 0;
     for (uint32_t i = 0; i < fs.n_world_prims; ++i) max_dfs_id_ = std::max(max_dfs_id_, fs.prims[i].dfs_id);
     // a flat scene that arrives without a tree (FlattenOptions::device_bvh, or a foreign host that has none) gets
@@ -1704,6 +1880,7 @@ void Renderer::build_bvh_device(int max_leaf_prims, BvhBuildStats* stats)
         S.total_ms = ms;
         view_.nodes = nodes;                 // the previous node array stays in scene_allocs until the next upload
         view_.n_nodes = S.n_nodes;
+        impl_->bvh_depth = S.depth;
     } catch (...) {
         for (void* p : bag) cudaFree(p);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -2033,11 +2210,9 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
     if (stats) *stats = S;
 }
 
-void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
-                           uint32_t* count_out, RenderStats* stats)
+void Renderer::ensure_frame(size_t n_pixels, float** accum, uint32_t** count, uint8_t** rgb)
 {
     CUDA_CHECK(cudaSetDevice(device_));
-    const size_t n_pixels = size_t(p.width) * size_t(p.height);
     Impl& I = *impl_;
     if (I.host_pixels < n_pixels) {
         if (I.host_accum) cudaFree(I.host_accum);
@@ -2049,17 +2224,177 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
         CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&I.host_rgb), n_pixels * 3));
         I.host_pixels = n_pixels;
     }
+    if (accum) *accum = I.host_accum;
+    if (count) *count = I.host_count;
+    if (rgb) *rgb = I.host_rgb;
+}
+
+void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
+                           uint32_t* count_out, RenderStats* stats)
+{
+    const size_t n_pixels = size_t(p.width) * size_t(p.height);
+    float* accum; uint32_t* count; uint8_t* rgb;
+    ensure_frame(n_pixels, &accum, &count, &rgb);
     RenderParams q = p;
     q.accumulate = 0;
     if (p.adaptive == 2) {
-        render_adaptive_squares(cam, q, I.host_rgb, I.host_accum, I.host_count, stats);
+        render_adaptive_squares(cam, q, rgb, accum, count, stats);
     } else {
-        render_device(cam, q, I.host_accum, I.host_count, stats, false);
-        resolve_device(I.host_accum, I.host_count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, I.host_rgb);
+        render_device(cam, q, accum, count, stats, false);
+        resolve_device(accum, count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, rgb);
     }
-    if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, I.host_rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
-    if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, I.host_accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
-    if (count_out) CUDA_CHECK(cudaMemcpy(count_out, I.host_count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
+    if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, accum, n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (count_out) CUDA_CHECK(cudaMemcpy(count_out, count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+}
+
+// ---- several GPUs in one process ------------------------------------------------------------------------------------
+// dst += the frames of up to 7 peers, read in place over NVLink (peer access) — the exchange of engine_mode::
+// parallel_images (engine.h:424-440: the four workers' float frames summed pixel by pixel) fused with nothing else because
+// nothing else follows it but write_color. 16-byte loads: a frame is W*H*3 floats (+ W*H counts), both multiples of 4
+// for every size the callers use; the tail is handled scalar.
+#define ARTB_MAX_GROUP 8
+struct PeerFrames { const float* accum[ARTB_MAX_GROUP - 1]; const uint32_t* count[ARTB_MAX_GROUP - 1]; int n; };
+
+__global__ void k_sum_peer_frames(float* accum, uint32_t* count, PeerFrames pf, size_t n_floats, size_t n_counts)
+{
+    const size_t stride = size_t(gridDim.x) * blockDim.x, tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t n4 = n_floats / 4;
+    for (size_t i = tid; i < n4; i += stride) {
+        float4 a = reinterpret_cast<float4*>(accum)[i];
+        for (int k = 0; k < pf.n; ++k) {
+            const float4 b = reinterpret_cast<const float4*>(pf.accum[k])[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(accum)[i] = a;
+    }
+    for (size_t i = n4 * 4 + tid; i < n_floats; i += stride) {
+        float a = accum[i];
+        for (int k = 0; k < pf.n; ++k) a += pf.accum[k][i];
+        accum[i] = a;
+    }
+    if (count)
+        for (size_t i = tid; i < n_counts; i += stride) {
+            uint32_t c = count[i];
+            for (int k = 0; k < pf.n; ++k) c += pf.count[k][i];
+            count[i] = c;
+        }
+}
+
+void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partition, const CameraParams& cam, const RenderParams& p,
+                                 uint8_t* rgb_out, float* accum_out, uint32_t* count_out, RenderStats* stats, RenderStats* per_device,
+                                 double* reduce_ms)
+{
+    if (n_peers < 0 || n_peers > ARTB_MAX_GROUP - 1) throw std::runtime_error("render_multi: at most 8 devices per group");
+    if (p.adaptive == 2) throw std::runtime_error("render_multi: the adaptive-squares mode runs on one device");
+    const int n = n_peers + 1;
+    const size_t n_pixels = size_t(p.width) * size_t(p.height);
+    std::vector<Renderer*> group{ this };
+    for (int k = 0; k < n_peers; ++k) group.push_back(peers[k]);
+    const size_t un = size_t(n);
+    std::vector<float*> accum(un, nullptr);
+    std::vector<uint32_t*> count(un, nullptr);
+    uint8_t* rgb = nullptr;
+    for (int k = 0; k < n; ++k) group[size_t(k)]->ensure_frame(n_pixels, &accum[size_t(k)], &count[size_t(k)], k == 0 ? &rgb : nullptr);
+
+    // every device renders its share from its own host thread (a context's calls are blocking)
+    std::vector<RenderStats> st(un);
+    std::vector<std::string> errors(un);
+    std::vector<std::thread> threads;
+    for (int k = 0; k < n; ++k) {
+        threads.emplace_back([&, k]() {
+            try {
+                RenderParams q = p;
+                q.accumulate = 0;
+                if (partition == 1) {                  // tiles: the whole sample range of this device's interleaved tiles
+                    q.tile_parts = n; q.tile_part = k;
+                } else {                               // samples: contiguous disjoint index ranges, shares differ by at most one
+                    const int base = p.samples_per_pixel / n, rest = p.samples_per_pixel % n;
+                    q.samples_per_pixel = base + (k < rest ? 1 : 0);
+                    q.sample_begin = p.sample_begin + k * base + std::min(k, rest);
+                    q.tile_parts = 1; q.tile_part = 0;
+                    if (p.adaptive) q.stream = p.stream + uint32_t(k);
+                }
+                if (q.samples_per_pixel < 1) {         // more devices than samples: this one has nothing to do
+                    CUDA_CHECK(cudaSetDevice(group[size_t(k)]->device()));
+                    CUDA_CHECK(cudaMemset(accum[size_t(k)], 0, n_pixels * 3 * sizeof(float)));
+                    CUDA_CHECK(cudaMemset(count[size_t(k)], 0, n_pixels * sizeof(uint32_t)));
+                    return;
+                }
+                group[size_t(k)]->render_device(cam, q, accum[size_t(k)], count[size_t(k)], &st[size_t(k)], false);
+            } catch (const std::exception& e) {
+                errors[size_t(k)] = e.what();
+            }
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int k = 0; k < n; ++k)
+        if (!errors[size_t(k)].empty()) throw std::runtime_error("render_multi: device " + std::to_string(group[size_t(k)]->device()) + ": " + errors[size_t(k)]);
+
+    // the exchange: one kernel on this device reads the peers' frames where they lie
+    CUDA_CHECK(cudaSetDevice(device_));
+    cudaStream_t s0 = static_cast<cudaStream_t>(stream_);
+    Impl& I = *impl_;
+    PeerFrames pf{};
+    pf.n = n_peers;
+    std::vector<void*> staged;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0.f;
+    try {
+        for (int k = 0; k < n_peers; ++k) {
+            const int pd = peers[k]->device();
+            int can = 0;
+            if (pd != device_) CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device_, pd));
+            if (pd == device_) {
+                pf.accum[k] = accum[size_t(k + 1)]; pf.count[k] = count[size_t(k + 1)];      // two contexts on one GPU (tests)
+            } else if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+                cudaGetLastError();
+                pf.accum[k] = accum[size_t(k + 1)]; pf.count[k] = count[size_t(k + 1)];
+            } else {                                   // no peer access on this box: stage the frame on this device
+                float* a = dev_alloc<float>(staged, n_pixels * 3);
+                uint32_t* c = dev_alloc<uint32_t>(staged, n_pixels);
+                CUDA_CHECK(cudaMemcpyPeerAsync(a, device_, accum[size_t(k + 1)], pd, n_pixels * 3 * sizeof(float), s0));
+                CUDA_CHECK(cudaMemcpyPeerAsync(c, device_, count[size_t(k + 1)], pd, n_pixels * sizeof(uint32_t), s0));
+                pf.accum[k] = a; pf.count[k] = c;
+            }
+        }
+        CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaEventRecord(e0, s0));
+        if (n_peers) k_sum_peer_frames<<<I.sm_count * 4, 256, 0, s0>>>(accum[0], count[0], pf, n_pixels * 3, n_pixels);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaEventRecord(e1, s0));
+        CUDA_CHECK(cudaStreamSynchronize(s0));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    } catch (...) {
+        for (void* q : staged) cudaFree(q);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        throw;
+    }
+    for (void* q : staged) cudaFree(q);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (reduce_ms) *reduce_ms = ms;
+
+    // tiles: every pixel got the full spp from exactly one device; samples: the shares add up to spp — either way the
+    // summed frame holds spp samples per pixel in fixed mode, and `count` in the adaptive mode
+    resolve_device(accum[0], count[0], int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, rgb);
+    if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
+    if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, accum[0], n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (count_out) CUDA_CHECK(cudaMemcpy(count_out, count[0], n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+
+    RenderStats S;
+    for (int k = 0; k < n; ++k) {
+        const RenderStats& r = st[size_t(k)];
+        S.elapsed_ms = std::max(S.elapsed_ms, r.elapsed_ms);          // the devices run side by side
+        S.samples += r.samples; S.rays += r.rays; S.waves += r.waves; S.launches += r.launches;
+        S.overflow_rays += r.overflow_rays; S.pixels_active += r.pixels_active; S.pixels_converged += r.pixels_converged;
+        if (per_device) per_device[k] = r;
+    }
+    S.elapsed_ms += ms;
+    S.launches += n_peers ? 1 : 0;
+    if (stats) *stats = S;
 }
 
 } // namespace artb

@@ -99,6 +99,19 @@ public:
     void render_host(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_out, float* accum_out,
                      uint32_t* count_out, RenderStats* stats);
 
+    // ---- several GPUs in one process (artb_config::n_devices): engine_mode::parallel_images / parallel_stripes of the
+    // reference (engine.h:335-445: 4 workers, a final sum of their frames) with one B200 per worker.
+    // This renderer (device 0 of the group) and `peers` each render their share — partition 0: disjoint per-pixel
+    // sample ranges on their own Philox streams; partition 1: interleaved tiles — from their own host thread into their own
+    // frame; then ONE kernel on this device sums the peers' frames straight out of their memory over NVLink (peer loads;
+    // staged copies where peer access is unavailable), resolves and copies back. per_device (optional): one RenderStats
+    // per device, this one first.
+    void render_host_multi(Renderer* const* peers, int n_peers, int partition, const CameraParams& cam, const RenderParams& p,
+                           uint8_t* rgb_out, float* accum_out, uint32_t* count_out, RenderStats* stats, RenderStats* per_device,
+                           double* reduce_ms);
+    // grow-only device frame (W*H*3 float sums, W*H counts, W*H*3 bytes) of render_host / render_host_multi
+    void ensure_frame(size_t n_pixels, float** accum, uint32_t** count, uint8_t** rgb);
+
     void* stream() const { return stream_; }
     int device() const { return device_; }
 

@@ -601,7 +601,9 @@ ARTB_HD void collect_begin(Collector& c, bool has_tree)
 //   collect_pop   false when the walk has ended (nothing pending and the stack is empty)
 //   collect_node  enters the nearest pending child; the primitives of its leaf children that were hit are
 //                 prims[prim_base + b] for every set bit b of prim_mask (possibly none)
-ARTB_HD bool collect_pop(Collector& c, const uint2* stack)
+// Stack: anything indexable that yields uint2& — a lane-private array (uint2*), or k_traverse's shared-memory stack
+template <class Stack>
+ARTB_HD bool collect_pop(Collector& c, const Stack& stack)
 {
     if (c.ng.y <= 0x00ffffffu) {
         if (c.sp == 0) return false;
@@ -610,15 +612,16 @@ ARTB_HD bool collect_pop(Collector& c, const uint2* stack)
     return true;
 }
 
-template <class NodePtr>
-ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, uint2* stack,
-                          uint32_t& prim_base, uint32_t& prim_mask, float& tn_min, uint32_t one_bits, TraversalStats* stats)
+template <class NodePtr, class Stack>
+ARTB_HD void collect_node(NodePtr nodes, const BoxRay& br, float t_min_f, float t_max_f, Collector& c, Stack& stack,
+                          uint32_t& prim_base, uint32_t& prim_mask, float& tn_min, uint32_t one_bits, TraversalStats* stats,
+                          int stack_capacity = ARTB_STACK_DEPTH)
 {
     tn_min = INFINITY;
     const uint32_t hits = c.ng.y;
     const int bit = find_msb(hits);
     c.ng.y &= ~(1u << bit);
-    if (c.ng.y > 0x00ffffffu && c.sp < ARTB_STACK_DEPTH) stack[c.sp++] = c.ng;
+    if (c.ng.y > 0x00ffffffu && c.sp < stack_capacity) stack[c.sp++] = c.ng;
     const uint32_t slot = uint32_t(bit - 24) ^ (br.octinv4 & 0xffu);
     const uint32_t rel = uint32_t(pop_count(hits & ~(0xffffffffu << slot) & 0xffu));
     const uint4* q = reinterpret_cast<const uint4*>(nodes + (c.ng.x + rel));

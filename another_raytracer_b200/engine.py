@@ -210,19 +210,32 @@ class RenderOptions:
 
 
 def _stats_dict(s: _abi.Stats) -> dict:
-    return {name: getattr(s, name) for name, _ in _abi.Stats._fields_}
+    d = {name: getattr(s, name) for name, _ in _abi.Stats._fields_}
+    n = max(int(s.n_devices), 0)
+    d["device_ms"] = list(s.device_ms)[:n]
+    d["device_samples"] = list(s.device_samples)[:n]
+    return d
 
 
 class Context:
     """One GPU: artb_ctx."""
 
-    def __init__(self, device: int = 0, pool_paths: int = 0):
+    def __init__(self, device: int = 0, pool_paths: int = 0, devices: list | None = None, partition: str = "samples"):
+        """devices: several GPUs of this node behind one context (artb_config::devices): uploads replicate the scene,
+        render() splits the work (partition "samples" = engine_mode::parallel_images, "tiles" = parallel_stripes made
+        load-balanced) and sums the frames over NVLink on devices[0]."""
         lib = _abi.load()
         self._lib = lib
         self._h = C.c_void_p()
-        cfg = _abi.Config(device, pool_paths)
+        devs = list(devices) if devices else []
+        if len(devs) > _abi.MAX_DEVICES:
+            raise ValueError(f"at most {_abi.MAX_DEVICES} devices per context")
+        arr = (C.c_int32 * _abi.MAX_DEVICES)(*devs)
+        cfg = _abi.Config(devs[0] if devs else device, pool_paths, len(devs),
+                          _abi.PARTITION_TILES if partition == "tiles" else _abi.PARTITION_SAMPLES, arr)
         _check(lib.artb_create(C.byref(cfg), C.byref(self._h)))
         self.n_media = 0
+        self.n_devices = lib.artb_context_devices(self._h)
 
     def upload(self, scene: Scene):
         _check(self._lib.artb_upload_scene(self._h, scene._h), self._h)
@@ -341,13 +354,17 @@ class Engine:
 
     def __init__(self, cam: CameraDesc, mode: EngineMode = EngineMode.single, *, width: int, height: int,
                  samples_per_pixel: int = 100, max_depth: int = 50, seed: int = 1, device: int = 0,
-                 context: Context | None = None):
+                 context: Context | None = None, devices: list | None = None):
+        """devices: the reference's parallel modes use 4 worker threads (engine.h:335-445); here a worker is a GPU.
+        EngineMode.parallel_images splits the samples over `devices`, parallel_stripes the image (interleaved tiles);
+        without `devices` every mode renders on the one GPU `device`."""
         self.cam = cam
         self.mode = mode
         self.width, self.height = width, height
         self.samples_per_pixel, self.max_depth, self.seed = samples_per_pixel, max_depth, seed
         self._ctx = context
         self._device = device
+        self._devices = list(devices) if devices else None
         self._scene = None
         self.last_stats: dict = {}
 
@@ -355,7 +372,11 @@ class Engine:
         self._scene = scene
         if scene is not None and scene.info["top_level_objects"] > 0:
             if self._ctx is None:
-                self._ctx = Context(self._device)
+                if self._devices and self.mode in (EngineMode.parallel_images, EngineMode.parallel_stripes):
+                    self._ctx = Context(devices=self._devices,
+                                        partition="tiles" if self.mode is EngineMode.parallel_stripes else "samples")
+                else:
+                    self._ctx = Context(self._devices[0] if self._devices else self._device)
             self._ctx.upload(scene)
 
     def run(self, output_image: np.ndarray) -> int:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define ARTB_ABI_VERSION 1
+#define ARTB_ABI_VERSION 2     /* 2: artb_config carries a device list; artb_shade_batch, artb_camera_rays, artb_scene_from_graph */
 
 typedef enum artb_status {
     ARTB_OK = 0,
@@ -39,13 +39,30 @@ typedef struct artb_ctx artb_ctx;       /* one GPU + its path pool              
 typedef struct artb_scene artb_scene;   /* host scene graph + its flattened form */
 
 /* ---- context ------------------------------------------------------------------------------------ */
+#define ARTB_MAX_DEVICES 8
+typedef enum artb_partition {
+    ARTB_PARTITION_SAMPLES = 0,   /* every device renders all pixels with its share of the per-pixel samples on its own random
+                                     stream: engine_mode::parallel_images (engine.h:378-445, a sum of the workers' frames) */
+    ARTB_PARTITION_TILES = 1      /* interleaved tile_size x tile_size tiles, tile t on device t % n_devices: the load-balanced
+                                     form of engine_mode::parallel_stripes (engine.h:335-376, one row stripe per worker) */
+} artb_partition;
+
 typedef struct artb_config {
-    int32_t device;            /* CUDA device ordinal */
-    uint32_t pool_paths;       /* paths in flight (0 = default 2 Mi) */
+    int32_t device;            /* CUDA device ordinal (used when n_devices <= 1) */
+    uint32_t pool_paths;       /* paths in flight per device (0 = default 2 Mi) */
+    /* several GPUs of one node behind ONE context: the scene is replicated by artb_upload_*, artb_render splits
+       the work over the devices (one host thread each), sums the frames with one kernel that reads the peers' memory over
+       NVLink, and resolves on devices[0]. Every other call (trace / shade / device variants) runs on devices[0].
+       n_devices == 0 or 1: a single-device context on `device`. An ordinal may repeat (several path pools on one GPU). */
+    int32_t n_devices;         /* 0..ARTB_MAX_DEVICES */
+    int32_t partition;         /* artb_partition used by artb_render when n_devices > 1 */
+    int32_t devices[ARTB_MAX_DEVICES];
 } artb_config;
 
 int artb_abi_version(void);
+int artb_device_count(void);   /* CUDA devices visible to the process (0 without a GPU) */
 int artb_create(const artb_config* cfg, artb_ctx** out);
+int artb_context_devices(const artb_ctx* ctx);    /* devices behind this context (>= 1) */
 void artb_destroy(artb_ctx* ctx);
 /* message of the last failing call on this context (ctx may be NULL: last failure of a ctx-less call) */
 const char* artb_last_error(const artb_ctx* ctx);
@@ -212,6 +229,11 @@ typedef struct artb_stats {
     uint64_t h2d_bytes, d2h_bytes;
     double traverse_ms, pairs_ms, finish_ms;   /* profile=1: the kernels of the closest-hit stage (extend_ms = whole stage) */
     uint64_t overflow_rays;             /* rays traced by the one-phase overflow pass */
+    /* contexts with several devices: elapsed_ms = slowest device + the exchange; counts are summed over the devices */
+    int32_t n_devices, reserved;
+    double reduce_ms;                   /* the frame-sum kernel over peer memory */
+    double device_ms[ARTB_MAX_DEVICES]; /* CUDA-event time of every device's render */
+    uint64_t device_samples[ARTB_MAX_DEVICES];
 } artb_stats;
 
 /* rgb8_out: W*H*3 bytes, row 0 = top, RGB (the layout engine::run writes). accum_out (optional):

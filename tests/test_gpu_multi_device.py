@@ -1,0 +1,81 @@
+"""Several GPUs behind ONE context of the C ABI (SURVEY 8b / VERDICT r01 missing #6, #9): artb_config::devices, the scene
+replicated by artb_upload_scene, artb_render splitting the work and summing the frames with one kernel over peer memory —
+engine_mode::parallel_images / parallel_stripes of the reference (src/engine/engine.h:335-445: 4 workers + a final sum)
+with a GPU per worker. A device ordinal may repeat, so the whole path — worker threads, both partitions, the sum kernel,
+the adaptive mask across devices — is also exercised on a box with ONE GPU; with >= 2 GPUs (gpurun --gpus 2) the frames
+really cross NVLink."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _device_sets(artb):
+    sets = [[0, 0], [0, 0, 0]]
+    n = artb.load().artb_device_count()
+    if n >= 2:
+        sets.append(list(range(min(n, 4))))
+    return sets
+
+
+@pytest.mark.parametrize("partition", ["samples", "tiles"])
+def test_multi_device_render_equals_single_device_render(artb, partition):
+    """Philox is keyed by (pixel, sample): the union of the devices' shares IS the single-device render, whatever the split"""
+    scene = artb.Scene.build(8)
+    w, h, spp = 96, 80, 37                                    # spp not divisible by the device counts: shares differ by one
+    cam, opt = scene.camera(w, h), artb.RenderOptions(w, h, spp, seed=21)
+    one = artb.Context(0, 1 << 16)
+    one.upload(scene)
+    rgb1, st1, acc1, cnt1 = one.render(cam, opt, want_accum=True, want_count=True)
+    one.close()
+    for devices in _device_sets(artb):
+        ctx = artb.Context(pool_paths=1 << 16, devices=devices, partition=partition)
+        assert ctx.n_devices == len(devices)
+        ctx.upload(scene)
+        rgb, st, acc, cnt = ctx.render(cam, opt, want_accum=True, want_count=True)
+        assert st["n_devices"] == len(devices) and len(st["device_ms"]) == len(devices)
+        assert st["samples"] == st1["samples"] == w * h * spp and sum(st["device_samples"]) == st["samples"]
+        assert st["rays"] == st1["rays"], "same paths, wherever they were traced"
+        assert np.all(cnt == spp)
+        assert np.allclose(acc, acc1, rtol=1e-4, atol=1e-4)
+        assert np.mean(rgb != rgb1) < 1e-3
+        if partition == "samples":
+            assert max(st["device_samples"]) - min(st["device_samples"]) <= w * h
+        # the other entry points keep working on devices[0]
+        assert ctx.trace_batch(np.array([[478.0, 278, -600, -0.3, 0, 1, 0.5]])).shape == (1,)
+        ctx.close()
+
+
+def test_variance_mask_across_devices(artb):
+    """the adaptive mask with the image tiled over the devices: counts come back summed, every pixel owned by one device"""
+    scene = artb.Scene.build(5)
+    w, h = 120, 72
+    cam = scene.camera(w, h)
+    opt = artb.RenderOptions(w, h, 256, seed=2, mode=1, adaptive_min_spp=32, adaptive_batch_spp=32, adaptive_threshold=0.03, tile_size=16)
+    one = artb.Context(0, 1 << 16); one.upload(scene)
+    _, st1, acc1, cnt1 = one.render(cam, opt, want_accum=True, want_count=True)
+    one.close()
+    ctx = artb.Context(pool_paths=1 << 16, devices=_device_sets(artb)[-1], partition="tiles")
+    ctx.upload(scene)
+    _, st, acc, cnt = ctx.render(cam, opt, want_accum=True, want_count=True)
+    ctx.close()
+    assert cnt.min() >= 32 and cnt.max() <= 256 and st["samples"] == int(cnt.sum())
+    m1 = acc1.astype(np.float64) / np.maximum(cnt1, 1)[..., None]
+    m = acc.astype(np.float64) / np.maximum(cnt, 1)[..., None]
+    # the mask pools variance over 3x3 neighbourhoods, which differ at tile borders between the two runs: compare images
+    assert np.sqrt(np.mean((np.clip(m, 0, 4) - np.clip(m1, 0, 4)) ** 2)) < 0.05
+    assert abs(st["samples"] - st1["samples"]) < 0.15 * st1["samples"]
+
+
+def test_engine_parallel_modes_use_the_device_list(artb):
+    scene = artb.Scene.build(6)
+    out = {}
+    for mode in (artb.EngineMode.single, artb.EngineMode.parallel_images, artb.EngineMode.parallel_stripes):
+        eng = artb.Engine(scene.camera(72, 72), mode, width=72, height=72, samples_per_pixel=16, devices=[0, 0])
+        eng.set_scene(scene)
+        img = np.zeros(72 * 72 * 3, dtype=np.uint8)
+        assert eng.run(img) >= 0
+        assert eng.last_stats["n_devices"] == (1 if mode is artb.EngineMode.single else 2)
+        out[mode] = img.copy()
+    assert np.mean(out[artb.EngineMode.single] != out[artb.EngineMode.parallel_images]) < 1e-3
+    assert np.mean(out[artb.EngineMode.single] != out[artb.EngineMode.parallel_stripes]) < 1e-3

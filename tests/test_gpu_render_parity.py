@@ -86,7 +86,9 @@ def test_gpu_image_psnr_against_converged_oracle(artb, gpu_ctx, path):
     print(f"{path.stem}: PSNR(G, converged oracle) = {got:.2f} dB; fixture noise limit {fixture_psnr:.2f} dB")
     # expected: the fixture's noise plus the GPU image's own (4x the samples: +1 dB) plus 8-bit quantisation, which
     # dominates above ~48 dB; bound = 3 dB under the fixture's limit, the limit itself capped at 48 dB
-    assert got >= min(fixture_psnr, 48.0) - 3.0, f"PSNR(G, converged)={got:.2f} dB, fixture noise limit {fixture_psnr:.2f} dB"
+    # (matched sample counts: the GPU image carries as much noise as the fixture, the expected value is the limit - 3 dB)
+    slack = 3.0 if n > spp else 3.8
+    assert got >= min(fixture_psnr, 48.0) - slack, f"PSNR(G, converged)={got:.2f} dB, fixture noise limit {fixture_psnr:.2f} dB"
     if fixture_psnr >= 43.0:
         assert got >= 40.0
     if alias in (6, 7, 8):
@@ -165,7 +167,7 @@ def test_variance_mask_against_converged_oracle(artb, gpu_ctx, alias):
     cam = scene.camera(w, h)
     cap = 16384
     _, st, acc, cnt = gpu_ctx.render(cam, artb.RenderOptions(w, h, cap, seed=5, mode=1, adaptive_min_spp=256, adaptive_batch_spp=256,
-                                                             adaptive_threshold=0.004), want_accum=True, want_count=True)
+                                                             adaptive_threshold=0.02), want_accum=True, want_count=True)
     adaptive = acc.astype(np.float64) / np.maximum(cnt, 1)[..., None]
     mean_spp = st["samples"] / (w * h)
     fixed_spp = max(int(mean_spp), 1)
