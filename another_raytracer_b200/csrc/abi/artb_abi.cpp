@@ -509,13 +509,12 @@ int artb_render(artb_ctx* ctx, const artb_camera* cam, const artb_render_params*
         const size_t n_dev = 1 + ctx->peers.size();
         std::vector<RenderStats> per(n_dev);
         double reduce_ms = 0;
-        if (n_dev > 1 && p->mode != ARTB_MODE_ADAPTIVE_SQUARES) {
+        if (n_dev > 1) {
             std::vector<Renderer*> peers;
             for (auto& r : ctx->peers) peers.push_back(r.get());
             ctx->renderer->render_host_multi(peers.data(), int(peers.size()), ctx->partition, make_camera(*cam), to_params(*p), rgb8_out,
                                              accum_out, count_out, &s, per.data(), &reduce_ms);
         } else {
-            // one device, and the reference's own adaptive strategy (a serial refinement of squares): devices[0]
             ctx->renderer->render_host(make_camera(*cam), to_params(*p), rgb8_out, accum_out, count_out, &s);
             per[0] = s;
         }

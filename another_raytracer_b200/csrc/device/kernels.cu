@@ -2139,10 +2139,75 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (stats) *stats = S;
 }
 
+// ---- several GPUs in one process: the exchange -----------------------------------------------------------------------
+// dst += the frames of up to 7 peers, read in place over NVLink (peer access) — the exchange of engine_mode::
+// parallel_images (engine.h:424-440: the four workers' float frames summed pixel by pixel) fused with nothing else because
+// nothing else follows it but write_color. 16-byte loads; the tail is handled scalar.
+#define ARTB_MAX_GROUP 8
+struct PeerFrames { const float* accum[ARTB_MAX_GROUP - 1]; const uint32_t* count[ARTB_MAX_GROUP - 1]; int n; };
+
+__global__ void k_sum_peer_frames(float* accum, uint32_t* count, PeerFrames pf, size_t n_floats, size_t n_counts)
+{
+    const size_t stride = size_t(gridDim.x) * blockDim.x, tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t n4 = n_floats / 4;
+    for (size_t i = tid; i < n4; i += stride) {
+        float4 a = reinterpret_cast<float4*>(accum)[i];
+        for (int k = 0; k < pf.n; ++k) {
+            const float4 b = reinterpret_cast<const float4*>(pf.accum[k])[i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(accum)[i] = a;
+    }
+    for (size_t i = n4 * 4 + tid; i < n_floats; i += stride) {
+        float a = accum[i];
+        for (int k = 0; k < pf.n; ++k) a += pf.accum[k][i];
+        accum[i] = a;
+    }
+    if (count)
+        for (size_t i = tid; i < n_counts; i += stride) {
+            uint32_t c = count[i];
+            for (int k = 0; k < pf.n; ++k) c += pf.count[k][i];
+            count[i] = c;
+        }
+}
+
+// Frames of the peers as device `self` can read them: in place where peer access exists (or the peer is the same GPU),
+// else staged on `self` (copies queued on s0, buffers appended to `staged` for the caller to free).
+static PeerFrames reachable_frames(int self, cudaStream_t s0, Renderer* const* peers, int n_peers, float* const* accum,
+                                   uint32_t* const* count, size_t n_pixels, bool with_count, std::vector<void*>& staged)
+{
+    PeerFrames pf{};
+    pf.n = n_peers;
+    for (int k = 0; k < n_peers; ++k) {
+        const int pd = peers[k]->device();
+        int can = pd == self ? 1 : 0;
+        if (pd != self) CUDA_CHECK(cudaDeviceCanAccessPeer(&can, self, pd));
+        if (can) {
+            if (pd != self) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
+                cudaGetLastError();
+            }
+            pf.accum[k] = accum[k]; pf.count[k] = with_count ? count[k] : nullptr;
+        } else {
+            float* a = dev_alloc<float>(staged, n_pixels * 3);
+            CUDA_CHECK(cudaMemcpyPeerAsync(a, self, accum[k], pd, n_pixels * 3 * sizeof(float), s0));
+            pf.accum[k] = a; pf.count[k] = nullptr;
+            if (with_count) {
+                uint32_t* c = dev_alloc<uint32_t>(staged, n_pixels);
+                CUDA_CHECK(cudaMemcpyPeerAsync(c, self, count[k], pd, n_pixels * sizeof(uint32_t), s0));
+                pf.count[k] = c;
+            }
+        }
+    }
+    return pf;
+}
+
 // engine_mode::adaptive of the reference (engine.h:151-333), level by level (adaptive_squares.cuh)
 void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_dev, float* accum_dev,
-                                       uint32_t* count_dev, RenderStats* stats)
+                                       uint32_t* count_dev, RenderStats* stats, Renderer* const* peers, int n_peers)
 {
+    if (n_peers < 0 || n_peers > ARTB_MAX_GROUP - 1) throw std::runtime_error("render: at most 8 devices per group");
     if (!has_scene_) throw std::runtime_error("render: no scene uploaded");
     constexpr int kBig = 12;
     if (p.width % kBig != 0 || p.height % kBig != 0 || p.width > 65535 || p.height > 65535)   // engine.h:182-183
@@ -2173,7 +2238,62 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
         q.adaptive = 0; q.accumulate = 1; q.tile_parts = 1; q.tile_part = 0;
         for (int size = kBig; ; size /= 2) {
             // trace the pixels this level asked for, at full spp
-            if (n_px) {
+            if (n_px && n_peers > 0) {
+                // this level's pixels, split evenly over the group: every device traces its slice at full spp (the peers
+                // into their own zeroed frames), then the peers' frames are added to this one over peer memory
+                CUDA_CHECK(cudaStreamSynchronize(st));                     // the list is complete
+                const int n = n_peers + 1;
+                std::vector<RenderStats> rs(static_cast<size_t>(n));
+                std::vector<std::string> errors(static_cast<size_t>(n));
+                std::vector<float*> pacc(static_cast<size_t>(n_peers), nullptr);
+                std::vector<uint32_t*> pcnt(static_cast<size_t>(n_peers), nullptr);
+                std::vector<std::thread> threads;
+                for (int k = 0; k < n; ++k) {
+                    threads.emplace_back([&, k]() {
+                        try {
+                            const uint32_t b = uint32_t(uint64_t(n_px) * uint64_t(k) / uint64_t(n));
+                            const uint32_t e = uint32_t(uint64_t(n_px) * uint64_t(k + 1) / uint64_t(n));
+                            RenderParams qq = q;
+                            qq.n_pixel_list = e - b;
+                            if (k == 0) {
+                                qq.pixel_list_dev = L.pixels + b;
+                                if (e > b) render_device(cam, qq, accum_dev, nullptr, &rs[0], false);
+                                return;
+                            }
+                            Renderer* pr = peers[k - 1];
+                            pr->ensure_frame(n_pixels, &pacc[size_t(k - 1)], &pcnt[size_t(k - 1)], nullptr);
+                            CUDA_CHECK(cudaSetDevice(pr->device()));
+                            // the slice of the list travels into the peer's (otherwise unused) count frame
+                            uint32_t* list_k = pcnt[size_t(k - 1)];
+                            if (e > b) CUDA_CHECK(cudaMemcpyPeer(list_k, pr->device(), L.pixels + b, device_, size_t(e - b) * sizeof(uint32_t)));
+                            qq.pixel_list_dev = list_k;
+                            qq.accumulate = 0;
+                            if (e > b) pr->render_device(cam, qq, pacc[size_t(k - 1)], nullptr, &rs[size_t(k)], false);
+                            else CUDA_CHECK(cudaMemset(pacc[size_t(k - 1)], 0, n_pixels * 3 * sizeof(float)));
+                        } catch (const std::exception& ex) {
+                            errors[size_t(k)] = ex.what();
+                        }
+                    });
+                }
+                for (auto& t : threads) t.join();
+                for (int k = 0; k < n; ++k)
+                    if (!errors[size_t(k)].empty()) throw std::runtime_error("adaptive squares, device share " + std::to_string(k) + ": " + errors[size_t(k)]);
+                CUDA_CHECK(cudaSetDevice(device_));
+                std::vector<void*> staged;
+                try {
+                    const PeerFrames pf = reachable_frames(device_, st, peers, n_peers, pacc.data(), pcnt.data(), n_pixels, false, staged);
+                    k_sum_peer_frames<<<impl_->sm_count * 4, 256, 0, st>>>(accum_dev, nullptr, pf, n_pixels * 3, 0);
+                    CUDA_CHECK(cudaGetLastError());
+                    CUDA_CHECK(cudaStreamSynchronize(st));
+                } catch (...) {
+                    for (void* x : staged) cudaFree(x);
+                    throw;
+                }
+                for (void* x : staged) cudaFree(x);
+                for (const RenderStats& r : rs) { S.samples += r.samples; S.rays += r.rays; S.waves = std::max(S.waves, r.waves); S.launches += r.launches; }
+                S.launches++;
+                k_sq_commit<<<(n_px + 255) / 256, 256, 0, st>>>(L.pixels, n_px, accum_dev, p.samples_per_pixel, work, count_dev);
+            } else if (n_px) {
                 q.pixel_list_dev = L.pixels; q.n_pixel_list = n_px;
                 RenderStats r;
                 render_device(cam, q, accum_dev, nullptr, &r, false);
@@ -2248,45 +2368,29 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
     if (count_out) CUDA_CHECK(cudaMemcpy(count_out, count, n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost));
 }
 
-// ---- several GPUs in one process ------------------------------------------------------------------------------------
-// dst += the frames of up to 7 peers, read in place over NVLink (peer access) — the exchange of engine_mode::
-// parallel_images (engine.h:424-440: the four workers' float frames summed pixel by pixel) fused with nothing else because
-// nothing else follows it but write_color. 16-byte loads: a frame is W*H*3 floats (+ W*H counts), both multiples of 4
-// for every size the callers use; the tail is handled scalar.
-#define ARTB_MAX_GROUP 8
-struct PeerFrames { const float* accum[ARTB_MAX_GROUP - 1]; const uint32_t* count[ARTB_MAX_GROUP - 1]; int n; };
-
-__global__ void k_sum_peer_frames(float* accum, uint32_t* count, PeerFrames pf, size_t n_floats, size_t n_counts)
-{
-    const size_t stride = size_t(gridDim.x) * blockDim.x, tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const size_t n4 = n_floats / 4;
-    for (size_t i = tid; i < n4; i += stride) {
-        float4 a = reinterpret_cast<float4*>(accum)[i];
-        for (int k = 0; k < pf.n; ++k) {
-            const float4 b = reinterpret_cast<const float4*>(pf.accum[k])[i];
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        reinterpret_cast<float4*>(accum)[i] = a;
-    }
-    for (size_t i = n4 * 4 + tid; i < n_floats; i += stride) {
-        float a = accum[i];
-        for (int k = 0; k < pf.n; ++k) a += pf.accum[k][i];
-        accum[i] = a;
-    }
-    if (count)
-        for (size_t i = tid; i < n_counts; i += stride) {
-            uint32_t c = count[i];
-            for (int k = 0; k < pf.n; ++k) c += pf.count[k][i];
-            count[i] = c;
-        }
-}
-
+// ---- several GPUs in one process: the render ----------------------------------------------------------------------------
 void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partition, const CameraParams& cam, const RenderParams& p,
                                  uint8_t* rgb_out, float* accum_out, uint32_t* count_out, RenderStats* stats, RenderStats* per_device,
                                  double* reduce_ms)
 {
     if (n_peers < 0 || n_peers > ARTB_MAX_GROUP - 1) throw std::runtime_error("render_multi: at most 8 devices per group");
-    if (p.adaptive == 2) throw std::runtime_error("render_multi: the adaptive-squares mode runs on one device");
+    if (p.adaptive == 2) {
+        // the reference's own adaptive strategy: the levels are serial, the pixels of a level are split over the devices
+        const size_t px = size_t(p.width) * size_t(p.height);
+        float* a; uint32_t* c; uint8_t* rgb8;
+        ensure_frame(px, &a, &c, &rgb8);
+        RenderParams q = p;
+        q.accumulate = 0;
+        RenderStats S;
+        render_adaptive_squares(cam, q, rgb8, a, c, &S, peers, n_peers);
+        if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, rgb8, px * 3, cudaMemcpyDeviceToHost));
+        if (accum_out) CUDA_CHECK(cudaMemcpy(accum_out, a, px * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+        if (count_out) CUDA_CHECK(cudaMemcpy(count_out, c, px * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (stats) *stats = S;
+        if (per_device) per_device[0] = S;
+        if (reduce_ms) *reduce_ms = 0;
+        return;
+    }
     const int n = n_peers + 1;
     const size_t n_pixels = size_t(p.width) * size_t(p.height);
     std::vector<Renderer*> group{ this };
@@ -2336,30 +2440,11 @@ void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partit
     cudaStream_t s0 = static_cast<cudaStream_t>(stream_);
     Impl& I = *impl_;
     PeerFrames pf{};
-    pf.n = n_peers;
     std::vector<void*> staged;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     float ms = 0.f;
     try {
-        for (int k = 0; k < n_peers; ++k) {
-            const int pd = peers[k]->device();
-            int can = 0;
-            if (pd != device_) CUDA_CHECK(cudaDeviceCanAccessPeer(&can, device_, pd));
-            if (pd == device_) {
-                pf.accum[k] = accum[size_t(k + 1)]; pf.count[k] = count[size_t(k + 1)];      // two contexts on one GPU (tests)
-            } else if (can) {
-                const cudaError_t e = cudaDeviceEnablePeerAccess(pd, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_CHECK(e);
-                cudaGetLastError();
-                pf.accum[k] = accum[size_t(k + 1)]; pf.count[k] = count[size_t(k + 1)];
-            } else {                                   // no peer access on this box: stage the frame on this device
-                float* a = dev_alloc<float>(staged, n_pixels * 3);
-                uint32_t* c = dev_alloc<uint32_t>(staged, n_pixels);
-                CUDA_CHECK(cudaMemcpyPeerAsync(a, device_, accum[size_t(k + 1)], pd, n_pixels * 3 * sizeof(float), s0));
-                CUDA_CHECK(cudaMemcpyPeerAsync(c, device_, count[size_t(k + 1)], pd, n_pixels * sizeof(uint32_t), s0));
-                pf.accum[k] = a; pf.count[k] = c;
-            }
-        }
+        pf = reachable_frames(device_, s0, peers, n_peers, accum.data() + 1, count.data() + 1, n_pixels, true, staged);
         CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0, s0));
         if (n_peers) k_sum_peer_frames<<<I.sm_count * 4, 256, 0, s0>>>(accum[0], count[0], pf, n_pixels * 3, n_pixels);

@@ -90,8 +90,10 @@ public:
                        RenderStats* stats, bool profile);
     // engine_mode::adaptive of the reference (engine.h:151-333): corners of 12/6/3-pixel squares traced at full spp,
     // the rest interpolated. Device buffers: rgb W*H*3, accum W*H*3 sums of the traced pixels, count = spp where traced.
+    // peers (optional): the pixels each level asks for are split evenly over this device and the peers; their frames are
+    // summed into accum_dev over peer memory before the level's pixels are committed.
     void render_adaptive_squares(const CameraParams& cam, const RenderParams& p, uint8_t* rgb_dev, float* accum_dev,
-                                 uint32_t* count_dev, RenderStats* stats);
+                                 uint32_t* count_dev, RenderStats* stats, Renderer* const* peers = nullptr, int n_peers = 0);
     // write_color (color.h:6-22) over accum/count -> RGB8 (device buffers)
     void resolve_device(const float* accum_dev, const uint32_t* count_dev, int n_pixels, int fixed_spp, uint8_t* rgb_dev);
 

@@ -2,6 +2,7 @@
 
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -603,6 +604,8 @@ private:
         //    the interval short; g[4..9] keep the medium's world box for a cheap pre-test), and surfaces whose boxes span
         //    a large share of the scene (no divergence, and an early t_max for the traversal)
         std::vector<Item> globals, media, rest;
+        FlattenOptions opt = this->opt;
+        if (const char* e = std::getenv("ARTB_MAX_GLOBAL_PRIMS")) opt.max_global_prims = std::atoi(e);   // tuning knob
         for (const Item& it : world_items) {
             if (it.prim.type == PRIM_MEDIUM) {
                 Item m = it;

@@ -11,7 +11,7 @@
 //     ear-clipped the way mapbox/earcut 2.2.4 does for a hole-free ring of <80 points, then each output
 //     triangle has its first two indices swapped                         rapidobj.hpp Triangulate, n-gon branch
 //   * vertex positions and texcoords are parsed as float and widened to double (mesh.h:77-90).
-// tests/test_scene_parity.py compares the resulting triangle streams of cow/dino/capsule with the
+// tests/test_host_scene.py compares the resulting triangle streams of cow/dino/capsule with the
 // reference's own.
 #ifndef ARTB_HOST_MESH_H
 #define ARTB_HOST_MESH_H

@@ -3,7 +3,7 @@
 // Same entry point as the reference: scene_manager::build(scene_alias) -> scene
 // (reference: src/scene_manager.h:6-44, src/scene_manager.cpp:13-355). Aliases 1..9 are the reference's
 // scenes, rebuilt here with the same object order and the same draws from the global RNG, so the
-// resulting graphs are identical to the reference's down to the last bit (tests/test_scene_parity.py).
+// resulting graphs are identical to the reference's down to the last bit (tests/test_host_scene.py).
 // Added aliases (BASELINE.json configs 4 and 5):
 //   cow = 10, dino = 11   the reference's _mesh_scene assembly (scene_manager.cpp:236-258) around
 //                         models/cow.obj / models/dino.obj with the camera presets the reference keeps as

@@ -3,7 +3,7 @@
  * artb_scene_dump_graph() (include/artb.h) serialises a host scene graph in depth-first pre-order
  * as a flat array of doubles. The oracle glue (oracle/ref_glue/ref_tool.cpp) produces the same stream
  * from the UNMODIFIED reference's scene graph, so "our host scene construction == the reference's"
- * is a plain array comparison (tests/test_scene_parity.py).
+ * is a plain array comparison (tests/test_host_scene.py).
  *
  * Grammar (every item is a double; ints are stored exactly):
  *   LIST n  child*n                         reference: src/engine/hittable_list.h:9-24

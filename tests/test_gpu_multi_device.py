@@ -79,3 +79,24 @@ def test_engine_parallel_modes_use_the_device_list(artb):
         out[mode] = img.copy()
     assert np.mean(out[artb.EngineMode.single] != out[artb.EngineMode.parallel_images]) < 1e-3
     assert np.mean(out[artb.EngineMode.single] != out[artb.EngineMode.parallel_stripes]) < 1e-3
+
+
+def test_adaptive_squares_across_devices(artb):
+    """engine_mode::adaptive (engine.h:151-333) on a device group: the pixels every level asks for are split over the
+    devices; same pixels, same samples (Philox is keyed by pixel and sample), so the image is the single-device one up to
+    float summation order (which can flip a square's threshold decision on rare pixels)."""
+    scene = artb.Scene.build(6)
+    w, h, spp = 96, 96, 64
+    cam = scene.camera(w, h)
+    opt = artb.RenderOptions(w, h, spp, seed=8, mode=2)
+    one = artb.Context(0, 1 << 16); one.upload(scene)
+    rgb1, st1, _, cnt1 = one.render(cam, opt, want_count=True)
+    one.close()
+    for devices in _device_sets(artb):
+        ctx = artb.Context(pool_paths=1 << 16, devices=devices, partition="samples")
+        ctx.upload(scene)
+        rgb, st, _, cnt = ctx.render(cam, opt, want_count=True)
+        ctx.close()
+        assert np.mean(cnt != cnt1) < 0.01 and np.mean(rgb != rgb1) < 0.01
+        assert abs(int(st["samples"]) - int(st1["samples"])) <= 0.02 * st1["samples"]
+        assert 0 < st["samples"] < w * h * spp, "most pixels are interpolated, not traced"
