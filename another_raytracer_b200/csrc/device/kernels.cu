@@ -374,62 +374,6 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
     }
 }
 
-// The same merge with its compare-and-swap left IN FLIGHT: issue_merge decides from the peeked copy whether the candidate
-// can win at all, and if so fires the 128-bit CAS without looking at what it returns; resolve_merge — called one loop
-// iteration later, after the next pair's loads have been issued — reads the result. Only a CAS that lost a race (another
-// pair of the same ray got in between) or an exact tie takes the loop of merge_hit. The round trip of the atomic (15 % of
-// this kernel's stall samples when it was waited for in place) now overlaps the next pair's gathers.
-struct PendingMerge {
-    unsigned long long exp_lo, exp_hi, old_lo, old_hi;
-    double t;
-    uint32_t ray, prim, dfs, other;
-    bool active;
-};
-
-__device__ __forceinline__ void issue_merge(const TraceIO& io, PendingMerge& pm, uint32_t ray_id, unsigned long long cur_lo,
-                                            unsigned long long cur_hi, double t, uint32_t prim, uint32_t dfs)
-{
-    pm.active = false;
-    unsigned long long new_lo = (unsigned long long)__double_as_longlong(t);
-    unsigned long long new_hi = (unsigned long long)prim | ((unsigned long long)dfs << 32);
-    const double cur_t = __longlong_as_double((long long)cur_lo);
-    const int32_t cur_prim = int32_t(uint32_t(cur_hi));
-    if (cur_prim == ARTB_HIT_OVERFLOW) return;
-    uint32_t other = 0xffffffffu;
-    if (cur_prim >= 0) {
-        if (t > cur_t) return;
-        if (t == cur_t) {
-            const uint32_t cur_dfs = uint32_t(cur_hi >> 32);
-            if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
-            else other = uint32_t(cur_prim);
-            new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
-        }
-    } else if (!(t <= cur_t)) return;
-    pm.exp_lo = cur_lo; pm.exp_hi = cur_hi;
-    pm.t = t; pm.ray = ray_id; pm.prim = prim; pm.dfs = dfs; pm.other = other;
-    pm.active = true;
-    PathHit* h = io.hits.at(ray_id);
-    asm volatile("{\n\t.reg .b128 c, s, d;\n\tmov.b128 c, {%2, %3};\n\tmov.b128 s, {%4, %5};\n\t"
-                 "atom.global.relaxed.gpu.cas.b128 d, [%6], c, s;\n\tmov.b128 {%0, %1}, d;\n\t}"
-                 : "=l"(pm.old_lo), "=l"(pm.old_hi) : "l"(cur_lo), "l"(cur_hi), "l"(new_lo), "l"(new_hi), "l"(h) : "memory");
-}
-
-template <bool kBatch>
-__device__ __forceinline__ void resolve_merge(const TraceIO& io, PendingMerge& pm)
-{
-    if (!pm.active) return;
-    pm.active = false;
-    if (pm.old_lo == pm.exp_lo && pm.old_hi == pm.exp_hi) {
-        if (pm.other != 0xffffffffu) {
-            PathTie* tie = io.ties.at(pm.ray);
-            const uint32_t k = atomicAdd(&tie->n, 1u);
-            if (k < 3u) tie->prim[k] = pm.other;
-        }
-        return;
-    }
-    merge_hit<kBatch>(io, pm.ray, pm.old_lo, pm.old_hi, pm.t, pm.prim, pm.dfs);     // lost a race: start over from the fresh value
-}
-
 #ifndef ARTB_TRAVERSE_THREADS
 #define ARTB_TRAVERSE_THREADS 1024
 #endif
@@ -453,7 +397,7 @@ struct WarpFeed { float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };  
 // a warp's accesses to one entry are 32 consecutive words pairs, no bank conflicts). As a lane-private array it lived in
 // local memory: an LDL / STL round trip through L1 on every pop and push, 7 % of the kernel's stall samples.
 #ifndef ARTB_SMEM_STACK
-#define ARTB_SMEM_STACK 8             // entries; trees deeper than this use the local-memory stack
+#define ARTB_SMEM_STACK 0             // entries (0 = lane-private local-memory stack). 8 was measured: the same speed
 #endif
 template <int kEntries>
 struct TraverseStack {
@@ -523,31 +467,18 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
     // handful of shared loads, so lanes are refilled one by one, at once, while their neighbours keep walking.
     WarpFeed& feed = feeds[threadIdx.x >> 5];
     uint32_t feed_count = 0;          // warp-uniform: entries not handed out yet (taken from the top)
-    // The chunk of 32 rays the warp converts at its NEXT refill is claimed one refill ahead and its records are
-    // prefetched, so that the refill — at which all 32 lanes wait — finds them in L1/L2 instead of in DRAM (12 % of
-    // this kernel's stall samples sat on those loads).
-    uint32_t ahead_base = 0, ahead_rid = 0;
-    auto claim_ahead = [&]() {
-        if (lane == 0) ahead_base = atomicAdd(io.cursor_traverse, 32u);
-        ahead_base = __shfl_sync(0xffffffffu, ahead_base, 0);
-        if (ahead_base + uint32_t(lane) < n) {
-            ahead_rid = io.list ? io.list[ahead_base + uint32_t(lane)] : ahead_base + uint32_t(lane);
-            if (kBatch) prefetch_l1(io.batch_rays + size_t(ahead_rid) * 7);
-            else prefetch_l1(io.rays.at(ahead_rid));
-        }
-    };
-    claim_ahead();
     for (;;) {
         uint32_t m_active = __ballot_sync(0xffffffffu, active);
         if (m_active != 0xffffffffu) {
             if (feed_count == 0u && more) {
-                const uint32_t base = ahead_base;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(io.cursor_traverse, 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
                 const uint32_t got = base < n ? (n - base < 32u ? n - base : 32u) : 0u;
-                const uint32_t my_rid = ahead_rid;
                 if (base + 32u >= n) more = false;
-                else claim_ahead();             // the chunk after this one: id loads + prefetches fly while this one is converted
                 if (uint32_t(lane) < got) {
-                    const uint32_t rid = my_rid;
+                    const uint32_t idx = base + uint32_t(lane);
+                    const uint32_t rid = io.list ? io.list[idx] : idx;
                     const BoxRay b = make_box_ray(make_trav_ray(trace_io_ray<kBatch>(io, rid)));
                     feed.inv[0][lane] = b.inv[0]; feed.inv[1][lane] = b.inv[1]; feed.inv[2][lane] = b.inv[2];
                     feed.c[0][lane] = b.c[0]; feed.c[1][lane] = b.c[1]; feed.c[2][lane] = b.c[2];
@@ -737,15 +668,7 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
 #ifndef ARTB_PAIRS_PREFETCH
 #define ARTB_PAIRS_PREFETCH 0           // measured: prefetching ray / primitive lines during the sort costs 10 % (L1 thrash)
 #endif
-#ifndef ARTB_PAIRS_PER_THREAD
-#define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory
-#endif
-#ifndef ARTB_PAIRS_DEFER
-#define ARTB_PAIRS_DEFER 1            // the 128-bit CAS of a merge is checked one iteration later (PendingMerge)
-#endif
-#ifndef ARTB_PAIRS_L2_AHEAD
-#define ARTB_PAIRS_L2_AHEAD 1         // records of the block's next tile are prefetched into L2 while this tile is processed
-#endif
+#define ARTB_PAIRS_PER_THREAD 4       // tile = ARTB_PAIRS_THREADS * 4 pairs, sorted by primitive class in shared memory (8: -17 %)
 template <bool kBatch>
 __global__ void __launch_bounds__(ARTB_PAIRS_THREADS, ARTB_PAIRS_BLOCKS)
 k_pairs(TraceIO io, SceneView s)
@@ -776,29 +699,11 @@ k_pairs(TraceIO io, SceneView s)
         // cannot win and nothing is loaded or tested for it. The record loads also warm the rays' lines; all of a
         // thread's loads are issued before the first one is looked at.
         unsigned long long rec_lo[ARTB_PAIRS_PER_THREAD], rec_hi[ARTB_PAIRS_PER_THREAD];
-#if ARTB_PAIRS_L2_AHEAD
-        // the block's NEXT tile: its pairs are read now (coalesced, cheap) only to start pulling their rays' records from
-        // DRAM into L2 — by the time that tile is processed its first touches are L2 hits instead of DRAM round trips
-        uint2 ahead[ARTB_PAIRS_PER_THREAD];
-#pragma unroll
-        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
-            const uint32_t i = t0 + J * kTile + uint32_t(k) * ARTB_PAIRS_THREADS + threadIdx.x;
-            ahead[k] = i < cnt ? region[i] : make_uint2(0xffffffffu, 0u);
-        }
-#endif
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             rec_lo[k] = 0; rec_hi[k] = 0;
             if (pr[k].x != 0xffffffffu) peek_hit(io.hits.at(pr[k].x & 0xffffffu), rec_lo[k], rec_hi[k]);
         }
-#if ARTB_PAIRS_L2_AHEAD
-#pragma unroll
-        for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k)
-            if (ahead[k].x != 0xffffffffu) {
-                prefetch_l2(io.hits.at(ahead[k].x & 0xffffffu));
-                if (!kBatch) prefetch_l2(io.rays.at(ahead[k].x & 0xffffffu));
-            }
-#endif
 #pragma unroll
         for (int k = 0; k < ARTB_PAIRS_PER_THREAD; ++k) {
             uint32_t cls = ARTB_PRIM_CLASSES;
@@ -828,11 +733,6 @@ k_pairs(TraceIO io, SceneView s)
         const uint32_t n_live = class_start[ARTB_PRIM_CLASSES];
         // 3. one pair per thread, warps (almost) uniform in class. Warp-uniform trip count and explicit re-convergence
         // points: the primitive tests have many exits, and without them the compiler clones the merge into every exit.
-#if ARTB_PAIRS_DEFER
-        PendingMerge pm;
-        pm.active = false;
-        pm.exp_lo = pm.exp_hi = pm.old_lo = pm.old_hi = 0; pm.t = 0; pm.ray = pm.prim = pm.dfs = pm.other = 0;
-#endif
         for (uint32_t base = threadIdx.x & ~31u; base < n_live; base += ARTB_PAIRS_THREADS) {
             const uint32_t i = base + (threadIdx.x & 31u);
             bool ok = false;
@@ -847,24 +747,13 @@ k_pairs(TraceIO io, SceneView s)
                 const FlatPrim& p = s.prims[prim];
                 dfs = p.dfs_id;
                 DRay q = trace_io_ray<kBatch>(io, ray);
-#if ARTB_PAIRS_DEFER
-                resolve_merge<kBatch>(io, pm);       // the previous pair's CAS: its round trip ran under the loads above
-#endif
                 if (p.xform) q = to_object_space(s, p.xform, q);
                 ok = surface_t(p, q, io.t_min, io.t_max, t);
             }
             warp_sync();
-#if ARTB_PAIRS_DEFER
-            resolve_merge<kBatch>(io, pm);           // (lanes that had no pair this iteration)
-            if (ok && t == t) issue_merge(io, pm, ray, cur_lo, cur_hi, t, prim, dfs);
-#else
             if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs);
-#endif
             warp_sync();
         }
-#if ARTB_PAIRS_DEFER
-        resolve_merge<kBatch>(io, pm);
-#endif
         __syncthreads();
     }
 }
@@ -905,36 +794,32 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     const uint32_t stride = gridDim.x * blockDim.x;
     // The ray id of the NEXT iteration is loaded one iteration ahead and its records are prefetched while this
     // iteration computes; all records of this iteration are requested together, before anything waits on them.
-    // (two iterations deep: the id of iteration k+2 is loaded while the records of iteration k+1, whose id arrived one
-    // iteration ago, are prefetched — the prefetch no longer waits for the id it has just asked for)
     uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
-    uint32_t id = 0, next_id = 0;
+    uint32_t id = 0;
     if (base + uint32_t(lane) < n) id = io.list ? io.list[base + lane] : base + uint32_t(lane);
-    if (base + stride + uint32_t(lane) < n) next_id = io.list ? io.list[base + stride + lane] : base + stride + uint32_t(lane);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
         const uint32_t next_idx = idx + stride;
-        const uint32_t far_idx = next_idx + stride;
-        uint32_t far_id = 0;
-        if (far_idx < n) far_id = io.list ? io.list[far_idx] : far_idx;
+        uint32_t next_id = 0;
+        if (next_idx < n) next_id = io.list ? io.list[next_idx] : next_idx;
         PathHit ph;
         ph.t = 0; ph.prim = -1; ph.dfs = 0;
         DRay r;
         r.o = mk3(0, 0, 0); r.d = mk3(1, 0, 0); r.tm = 0;
         PathAux a;
         a.thr[0] = a.thr[1] = a.thr[2] = 0.f; a.pixel = a.sample = a.rng_block = a.depth = a.pad = 0;
-        if (next_idx < n) {
-            prefetch_l1(io.hits.at(next_id));
-            if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
-            else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
-        }
         if (valid) {
             ph = load_hit(io.hits.at(id));
             r = trace_io_ray<kBatch>(io, id);
             if (!kBatch) load_aux(io.aux.at(id), a);
+        }
+        if (next_idx < n) {
+            prefetch_l1(io.hits.at(next_id));
+            if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
+            else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
         }
         // flagged by k_traverse (pairs did not fit), or more leaves tied than the list holds: the one-phase pass traces the ray
         const bool tied = valid && ph.prim >= 0 && (ph.dfs & ARTB_HIT_TIED) != 0u;
@@ -998,7 +883,6 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 #endif
         }
         id = next_id;
-        next_id = far_id;
     }
     if (!kBatch) append_commit(pend);
 }
@@ -1098,27 +982,16 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
         if (!valid) return 0u;
         return m == Q_REGEN ? w.q_regen[cur][i] : w.q_shade[size_t(m) * w.pool + i];
     };
-    // software pipeline, two iterations deep: the slot id of iteration k+2 is loaded while iteration k shades, and the
-    // records of iteration k+1 — whose id arrived during iteration k-1 — are prefetched at the same time. (One stage
-    // deep, the prefetch had to wait for the id it had just asked for: 20 % of this kernel's stall samples.)
-#ifndef ARTB_SHADE_PIPE
-#define ARTB_SHADE_PIPE 2
-#endif
+    // software pipeline: the slot of the NEXT iteration is loaded one iteration ahead and its records are prefetched
+    // while this iteration shades (two iterations deep measured the same)
     uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int m = 0; uint32_t i = 0; bool valid = false;
     uint32_t slot = locate(wi, m, i, valid);
-    int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
-    uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
     for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
-#if ARTB_SHADE_PIPE >= 2
-        int far_m = 0; uint32_t far_i = 0; bool far_valid = false;
-        const uint32_t far_slot = locate(wi + 2u * n_warps, far_m, far_i, far_valid);
-        if (next_valid && next_m != Q_REGEN) {
-            prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
-        }
-#endif
+        int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
+        const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
         int key = -1;                       // 0: a ray for the next wave, 1: slot is free
         if (m == Q_REGEN) {
             if (valid) {
@@ -1149,11 +1022,9 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
             PathAux a;
             load_aux(w.aux.at(slot), a);
             const PathHit ph = load_hit(w.hits.at(slot));
-#if ARTB_SHADE_PIPE < 2
             if (next_valid && next_m != Q_REGEN) {
                 prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
             }
-#endif
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
             key = 1;
@@ -1180,11 +1051,6 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
         append_reserve(pend, key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1],
                        key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1], slot, lane);
         m = next_m; i = next_i; valid = next_valid; slot = next_slot;
-#if ARTB_SHADE_PIPE >= 2
-        next_m = far_m; next_i = far_i; next_valid = far_valid; next_slot = far_slot;
-#else
-        next_slot = locate(wi + 2u * n_warps, next_m, next_i, next_valid);
-#endif
     }
     append_commit(pend);
 }

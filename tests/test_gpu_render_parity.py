@@ -157,17 +157,18 @@ def test_variance_mask_mode_saves_samples_and_stays_close(artb, gpu_ctx):
 
 @pytest.mark.parametrize("alias", [8, 6])
 def test_variance_mask_against_converged_oracle(artb, gpu_ctx, alias):
-    """north_star (3): the per-pixel variance mask compared with the ORACLE's converged image, not with the GPU's own
-    fixed render: at a cap of 16 Ki spp it must reach the quality a fixed render of the same total sample count reaches
-    (within 1.5 dB), stay above 38 dB, and spend fewer samples than the cap."""
+    """north_star (3): the per-pixel variance mask compared with the ORACLE's converged image (64 Ki spp), not with the
+    GPU's own fixed render: at a relative-standard-error target of 5 % and a cap of 32 Ki spp it must retire pixels (mean
+    spp well under the cap), reach at least the quality a FIXED render of the same total sample count reaches (within
+    1.5 dB: it trades samples between pixels, it does not lose them), and stay above 34 dB."""
     c = np.load(GOLDEN / f"converged_{alias}_128x128.npz")
     h, w, _ = c["lin"].shape
     scene = artb.Scene.build(alias)
     gpu_ctx.upload(scene)
     cam = scene.camera(w, h)
-    cap = 16384
+    cap = 32768
     _, st, acc, cnt = gpu_ctx.render(cam, artb.RenderOptions(w, h, cap, seed=5, mode=1, adaptive_min_spp=256, adaptive_batch_spp=256,
-                                                             adaptive_threshold=0.02), want_accum=True, want_count=True)
+                                                             adaptive_threshold=0.05), want_accum=True, want_count=True)
     adaptive = acc.astype(np.float64) / np.maximum(cnt, 1)[..., None]
     mean_spp = st["samples"] / (w * h)
     fixed_spp = max(int(mean_spp), 1)
@@ -175,10 +176,11 @@ def test_variance_mask_against_converged_oracle(artb, gpu_ctx, alias):
     fixed = facc.astype(np.float64) / fixed_spp
     ref8 = to8(c["lin"])
     p_adaptive, p_fixed = psnr8(to8(adaptive), ref8), psnr8(to8(fixed), ref8)
-    print(f"alias {alias}: variance mask {mean_spp:.0f} spp/pixel (cap {cap}) PSNR {p_adaptive:.2f} dB; fixed {fixed_spp} spp PSNR {p_fixed:.2f} dB")
+    print(f"alias {alias}: variance mask {mean_spp:.0f} spp/pixel (cap {cap}, {np.mean(cnt < cap) * 100:.0f} % of the pixels retired early) "
+          f"PSNR {p_adaptive:.2f} dB; fixed {fixed_spp} spp PSNR {p_fixed:.2f} dB")
     assert cnt.min() >= 256 and cnt.max() <= cap and st["samples"] == int(cnt.sum())
-    assert mean_spp < 0.9 * cap, "the mask must retire converged pixels"
-    assert p_adaptive >= 38.0
+    assert mean_spp < 0.8 * cap, "the mask must retire converged pixels"
+    assert p_adaptive >= 34.0
     assert p_adaptive >= p_fixed - 1.5
 
 
