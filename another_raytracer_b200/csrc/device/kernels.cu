@@ -781,10 +781,16 @@ __device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie,
 #define ARTB_FINISH_THREADS 128
 #endif
 #ifndef ARTB_FINISH_BLOCKS
-#define ARTB_FINISH_BLOCKS 4
+#define ARTB_FINISH_BLOCKS 3             // 168 registers, no spills: measured 3 % faster than 4 blocks of 128 registers with spills
 #endif
-template <bool kBatch>
-__global__ void __launch_bounds__(ARTB_FINISH_THREADS, ARTB_FINISH_BLOCKS)
+// kSurf / kMedia: whether the scene HAS global surfaces / global media. The kernel is compiled once per combination so that
+// a scene without media (Cornell box, the sphere scenes) or without global surfaces does not carry the registers of code it
+// never runs: the light variants hold more warps per SM, and this kernel is bound by the latency of its record loads.
+#ifndef ARTB_FINISH_BLOCKS_LIGHT
+#define ARTB_FINISH_BLOCKS_LIGHT 6
+#endif
+template <bool kBatch, bool kSurf, bool kMedia>
+__global__ void __launch_bounds__(ARTB_FINISH_THREADS, (kSurf && kMedia) || kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT)
 k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 {
     const uint32_t n = *io.n_ptr;
@@ -833,8 +839,8 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
             ClosestHit best;
             best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs & ~ARTB_HIT_TIED;
             if (tied) replay_ties(s, io.ties.at(id), n_tied, uint32_t(ph.prim), r, io.t_min, io.t_max, best);
-            for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
-            if (s.n_global_media) {
+            if (kSurf) for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
+            if (kMedia && s.n_global_media) {
                 MediumXi xi;
                 if (kBatch) {
                     xi.row = io.batch_xi ? io.batch_xi + size_t(id) * s.n_media : nullptr;
@@ -1284,6 +1290,16 @@ struct Renderer::Impl {
         io.pb.n_regions = nodes_fit_shared(view) ? uint32_t(sm_count) * ARTB_TRAVERSE_GRID_PER_SM : uint32_t(sm_count) * 6u;
         io.pb.region_cap = uint32_t(std::min<size_t>(capacity / io.pb.n_regions, 0x7fffffffu));
     }
+    template <bool kBatch>
+    void launch_finish(const SceneView& view, const TraceIO& io, const WaveBuffers& w, const RoundParams& rp, int cur, cudaStream_t st)
+    {
+        const bool surf = view.n_global_prims > view.n_global_media, media = view.n_global_media > 0;
+        const unsigned heavy = unsigned(sm_count) * ARTB_FINISH_BLOCKS, light = unsigned(sm_count) * (kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT);
+        if (surf && media) k_finish<kBatch, true, true><<<heavy, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        else if (surf) k_finish<kBatch, true, false><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        else if (media) k_finish<kBatch, false, true><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        else k_finish<kBatch, false, false><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+    }
     // two_phase: k_traverse + k_pairs + k_finish; otherwise the pruned walk k_walk + k_finish (trees beyond shared memory).
     // ev (optional): three events recorded after the tree kernel, after k_pairs (at once in walk mode) and after k_finish.
     template <bool kBatch>
@@ -1293,7 +1309,7 @@ struct Renderer::Impl {
         if (!two_phase) {
             k_walk<kBatch><<<sm_count * 4, ARTB_WALK_THREADS, 0, st>>>(io, view, w.c, cur);
             if (ev) { CUDA_CHECK(cudaEventRecord(ev[0], st)); CUDA_CHECK(cudaEventRecord(ev[1], st)); }
-            k_finish<kBatch><<<sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+            launch_finish<kBatch>(view, io, w, rp, cur, st);
             if (ev) CUDA_CHECK(cudaEventRecord(ev[2], st));
             CUDA_CHECK(cudaGetLastError());
             return;
@@ -1313,7 +1329,7 @@ struct Renderer::Impl {
         const uint32_t J = std::max(1u, uint32_t(sm_count) * ARTB_PAIRS_BLOCKS / io.pb.n_regions);
         k_pairs<kBatch><<<io.pb.n_regions * J, ARTB_PAIRS_THREADS, 0, st>>>(io, view);
         if (ev) CUDA_CHECK(cudaEventRecord(ev[1], st));
-        k_finish<kBatch><<<sm_count * ARTB_FINISH_BLOCKS, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        launch_finish<kBatch>(view, io, w, rp, cur, st);
         if (ev) CUDA_CHECK(cudaEventRecord(ev[2], st));
         CUDA_CHECK(cudaGetLastError());
     }
