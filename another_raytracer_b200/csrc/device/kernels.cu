@@ -774,6 +774,43 @@ __device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie,
     for (uint32_t k = 0; k <= n_tied; ++k) test_surface(s, cand[k], r, t_min, best);
 }
 
+// Queue appends of SEVERAL loop iterations with one atomic per queue: a warp parks the (queue, slot) of each of its last
+// kBatch iterations in shared memory and reserves the space for all of them at once — one returning atomicAdd per queue
+// that has entries, instead of one per queue and iteration. Every warp of the GPU appends to the same 2-6 counters; their
+// L2 atomic unit serialises same-address updates (tools/atomic_probe.cu), so the NUMBER of atomics, not their latency, is
+// what the append costs. keys[j][t] < 0: no entry.
+template <int kBatch, int kThreads, class QueueOf>
+__device__ __forceinline__ void flush_batched_appends(int (*keys)[kThreads], uint32_t (*values)[kThreads], int n_iter, int n_queues,
+                                                      uint32_t* counters, QueueOf queue_of, int lane)
+{
+    const uint32_t lt = (1u << lane) - 1u;
+    int key[kBatch];
+    uint32_t val[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+        key[j] = j < n_iter ? keys[j][threadIdx.x] : -1;
+        val[j] = j < n_iter ? values[j][threadIdx.x] : 0u;
+    }
+    for (int q = 0; q < n_queues; ++q) {
+        uint32_t m[kBatch], total = 0;
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) { m[j] = __ballot_sync(0xffffffffu, key[j] == q); total += uint32_t(__popc(m[j])); }
+        if (total == 0u) continue;                     // warp-uniform
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(counters + q, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        uint32_t* dst = queue_of(q);
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            if (key[j] == q) dst[base + uint32_t(__popc(m[j] & lt))] = val[j];
+            base += uint32_t(__popc(m[j]));
+        }
+    }
+}
+
+#ifndef ARTB_FINISH_BATCH
+#define ARTB_FINISH_BATCH 4           // iterations per queue reservation in k_finish (1: reserve every iteration)
+#endif
 #ifndef ARTB_FINISH_DEFER
 #define ARTB_FINISH_DEFER 0           // deferred queue appends cost k_finish more in spills than the hidden latency gains
 #endif
@@ -784,10 +821,12 @@ __device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie,
 #define ARTB_FINISH_BLOCKS 3             // 168 registers, no spills: measured 3 % faster than 4 blocks of 128 registers with spills
 #endif
 // kSurf / kMedia: whether the scene HAS global surfaces / global media. The kernel is compiled once per combination so that
-// a scene without media (Cornell box, the sphere scenes) or without global surfaces does not carry the registers of code it
-// never runs: the light variants hold more warps per SM, and this kernel is bound by the latency of its record loads.
+// a scene without media (Cornell box, the sphere scenes) or without global surfaces (final scene, the meshes) does not carry
+// the code it never runs (Cornell box: -23 % on this kernel). Measured with the register budget varied per variant
+// (profiles/r02_finish_variants.txt): spills cost every variant more than the extra resident warps give back, so all of
+// them get the 168 registers of 3 blocks per SM.
 #ifndef ARTB_FINISH_BLOCKS_LIGHT
-#define ARTB_FINISH_BLOCKS_LIGHT 6
+#define ARTB_FINISH_BLOCKS_LIGHT ARTB_FINISH_BLOCKS
 #endif
 template <bool kBatch, bool kSurf, bool kMedia>
 __global__ void __launch_bounds__(ARTB_FINISH_THREADS, (kSurf && kMedia) || kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT)
@@ -805,6 +844,12 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     if (base + uint32_t(lane) < n) id = io.list ? io.list[base + lane] : base + uint32_t(lane);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
+#if ARTB_FINISH_BATCH > 1
+    __shared__ int s_keys[ARTB_FINISH_BATCH][ARTB_FINISH_THREADS];
+    __shared__ uint32_t s_ids[ARTB_FINISH_BATCH][ARTB_FINISH_THREADS];
+    int n_parked = 0;                  // warp-uniform: iterations parked since the last flush
+    auto queue_of = [&](int q) -> uint32_t* { return q == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(q) * w.pool; };
+#endif
     for (; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
@@ -876,7 +921,14 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
             }
         }
         if (!kBatch) {
-#if ARTB_FINISH_DEFER
+#if ARTB_FINISH_BATCH > 1
+            s_keys[n_parked][threadIdx.x] = key;
+            s_ids[n_parked][threadIdx.x] = id;
+            if (++n_parked == ARTB_FINISH_BATCH) {
+                flush_batched_appends<ARTB_FINISH_BATCH, ARTB_FINISH_THREADS>(s_keys, s_ids, n_parked, Q_OUT_COUNT, &c->n_out[cur][0], queue_of, lane);
+                n_parked = 0;
+            }
+#elif ARTB_FINISH_DEFER
             append_commit(pend);             // the previous iteration's entries: their atomics have long returned
             append_reserve(pend, key, &c->n_out[cur][key < 0 ? 0 : key],
                            key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key < 0 ? 0 : key) * w.pool, id, lane);
@@ -890,6 +942,9 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
         }
         id = next_id;
     }
+#if ARTB_FINISH_BATCH > 1
+    if (!kBatch && n_parked) flush_batched_appends<ARTB_FINISH_BATCH, ARTB_FINISH_THREADS>(s_keys, s_ids, n_parked, Q_OUT_COUNT, &c->n_out[cur][0], queue_of, lane);
+#endif
     if (!kBatch) append_commit(pend);
 }
 
@@ -959,6 +1014,9 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
 #ifndef ARTB_SHADE_BLOCKS
 #define ARTB_SHADE_BLOCKS 4
 #endif
+#ifndef ARTB_SHADE_BATCH
+#define ARTB_SHADE_BATCH 4            // iterations per queue reservation (1: the deferred per-iteration append)
+#endif
 __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w, SceneView s, RoundParams rp, int cur)
 {
     WaveCounters* c = w.c;
@@ -995,6 +1053,41 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
     uint32_t slot = locate(wi, m, i, valid);
     PendingAppend pend;
     pend.queue = nullptr; pend.value = pend.rank = pend.base_raw = 0; pend.leader = 0;
+#if ARTB_SHADE_BATCH > 1
+    // appends of ARTB_SHADE_BATCH iterations are reserved with ONE atomic per queue (flush_batched_appends): queue 0 = rays
+    // for the next wave (n_extend), queue 1 = free slots (n_out[.][Q_REGEN]); the two counters are 48 bytes apart
+    __shared__ int s_keys[ARTB_SHADE_BATCH][128];
+    __shared__ uint32_t s_slots[ARTB_SHADE_BATCH][128];
+    int n_parked = 0;
+    uint32_t* const ctr2 = &c->n_extend[cur ^ 1];
+    const int regen_off = int(&c->n_out[cur ^ 1][Q_REGEN] - ctr2);
+    auto flush = [&]() {
+        const uint32_t lt = (1u << lane) - 1u;
+        int key[ARTB_SHADE_BATCH]; uint32_t val[ARTB_SHADE_BATCH];
+#pragma unroll
+        for (int j = 0; j < ARTB_SHADE_BATCH; ++j) {
+            key[j] = j < n_parked ? s_keys[j][threadIdx.x] : -1;
+            val[j] = j < n_parked ? s_slots[j][threadIdx.x] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            uint32_t mk[ARTB_SHADE_BATCH], total = 0;
+#pragma unroll
+            for (int j = 0; j < ARTB_SHADE_BATCH; ++j) { mk[j] = __ballot_sync(0xffffffffu, key[j] == q); total += uint32_t(__popc(mk[j])); }
+            if (total == 0u) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(ctr2 + (q ? regen_off : 0), total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t* dst = q ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1];
+#pragma unroll
+            for (int j = 0; j < ARTB_SHADE_BATCH; ++j) {
+                if (key[j] == q) dst[base + uint32_t(__popc(mk[j] & lt))] = val[j];
+                base += uint32_t(__popc(mk[j]));
+            }
+        }
+        n_parked = 0;
+    };
+#endif
     for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
         int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
         const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
@@ -1053,11 +1146,20 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
                 }
             }
         }
+#if ARTB_SHADE_BATCH > 1
+        s_keys[n_parked][threadIdx.x] = key;
+        s_slots[n_parked][threadIdx.x] = slot;
+        if (++n_parked == ARTB_SHADE_BATCH) flush();
+#else
         append_commit(pend);                 // the previous iteration's entries: their atomics have long returned
         append_reserve(pend, key, key == 1 ? &c->n_out[cur ^ 1][Q_REGEN] : &c->n_extend[cur ^ 1],
                        key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1], slot, lane);
+#endif
         m = next_m; i = next_i; valid = next_valid; slot = next_slot;
     }
+#if ARTB_SHADE_BATCH > 1
+    if (n_parked) flush();
+#endif
     append_commit(pend);
 }
 
