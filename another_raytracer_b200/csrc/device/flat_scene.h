@@ -55,12 +55,13 @@ enum : uint32_t { TEX_SOLID = ARTB_TEX_SOLID, TEX_CHECKER = ARTB_TEX_CHECKER, TE
 // device-side view (all pointers are device pointers)
 // Code path a primitive takes in the double-precision test: k_pairs sorts each tile of pairs by it so that the lanes of
 // a warp run the same test (sphere / moving sphere / rect / triangle, each without or with a transform chain).
-#define ARTB_PRIM_CLASSES 8
+#define ARTB_PRIM_CLASSES 9           // 0-7: surfaces (below); 8: constant_medium pairs (k_traverse emits one per medium box a ray enters)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
 inline uint32_t prim_class_of(uint32_t type, uint32_t xform)
 {
+    if (type == PRIM_MEDIUM) return 8u;
     const uint32_t path = type == PRIM_SPHERE ? 0u : type == PRIM_MSPHERE ? 1u : type == PRIM_TRIANGLE ? 3u : 2u;
     return path * 2u + (xform ? 1u : 0u);
 }

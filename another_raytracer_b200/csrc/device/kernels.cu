@@ -282,6 +282,10 @@ struct TraceIO {
     double t_min, t_max;
     Strided<PathRay> rays;            // wave mode: the path pool
     Strided<PathAux> aux;
+    uint32_t seed, stream;            // wave mode: Philox key of the render (the media's draws: MediumXi)
+    const SceneView* scene_dev;       // the SceneView in global memory (for out-of-line device functions)
+    uint32_t media_pairs;             // 1: k_traverse emits a (ray, medium) pair per medium box the ray enters and k_pairs
+                                      // runs constant_medium::hit; 0: k_finish tests the media ray by ray
     const double* batch_rays;         // batch mode: n * 7 doubles
     const double* batch_xi;           // batch mode: n * n_media explicit medium draws, or nullptr
     HitRecordOut* batch_out;
@@ -342,9 +346,12 @@ __device__ __forceinline__ bool cas_hit(PathHit* h, unsigned long long& cur_lo, 
 // million rays. The record keeps the later leaf and gets ARTB_HIT_TIED set, the other leaf goes to the ray's tie list;
 // k_finish — which has the ray — replays the tied leaves in the reference's order.
 #define ARTB_HIT_TIED 0x80000000u     // bit 31 of PathHit::dfs
+// A constant_medium on either side of an exact tie: the later one in the reference's order wins (every leaf, a medium
+// included, accepts t == t_max: constant_medium.h:52-69 clamps its interval to t_max and keeps a scatter point AT the end);
+// the reference-bvh-box subtlety of surface ties (tie_later_wins) does not arise: media sit in plain lists. Decided here.
 template <bool kBatch>
 __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, unsigned long long cur_lo, unsigned long long cur_hi,
-                                          double t, uint32_t prim, uint32_t dfs)
+                                          double t, uint32_t prim, uint32_t dfs, const uint8_t* prim_class = nullptr, bool is_medium = false)
 {
     PathHit* h = io.hits.at(ray_id);
     for (;;) {
@@ -358,9 +365,14 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
             if (t > cur_t) return;
             if (t == cur_t) {
                 const uint32_t cur_dfs = uint32_t(cur_hi >> 32);
-                if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
-                else other = uint32_t(cur_prim);
-                new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
+                if (prim_class && (is_medium || prim_class[cur_prim] == 8u)) {
+                    if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) return;          // the record's leaf comes later: it stays
+                    new_hi |= cur_hi & ((unsigned long long)ARTB_HIT_TIED << 32);   // surface ties already noted stay noted
+                } else {
+                    if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
+                    else other = uint32_t(cur_prim);
+                    new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
+                }
             }
         } else if (!(t <= cur_t)) return;
         if (cas_hit(h, cur_lo, cur_hi, new_lo, new_hi)) {
@@ -486,6 +498,20 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
                     feed.id[lane] = rid;
                     store_hit(io.hits.at(rid), io.t_max, -1, 0u);
                     io.ties.at(rid)->n = 0u;
+                    if (io.media_pairs) {
+                        // one pair per constant_medium whose world box the ray enters (here, with all lanes of the warp
+                        // busy): k_pairs runs constant_medium::hit on them next to the surface tests
+                        for (uint32_t mi = s.n_global_prims - s.n_global_media; mi < s.n_global_prims; ++mi) {
+                            const FlatPrim& mp = s.prims[mi];
+                            const float lo[3] = { d2f_rd(mp.g[4]), d2f_rd(mp.g[5]), d2f_rd(mp.g[6]) };
+                            const float hi[3] = { d2f_ru(mp.g[7]), d2f_ru(mp.g[8]), d2f_ru(mp.g[9]) };
+                            float tn = 0.f;
+                            if (!slab_box(lo, hi, b, t_min_f, t_max_f, &tn)) continue;
+                            const uint32_t pos = atomicAdd(&s_pairs, 1u);
+                            if (pos < cap) region[pos] = pack_pair(rid, mi, tn);
+                            else mark_overflow(io.hits.at(rid));       // region full: the one-phase pass traces this ray
+                        }
+                    }
                 }
                 __syncwarp();
                 feed_count = got;
@@ -570,8 +596,11 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
 // stays full. The global surfaces, the media and the binning are left to k_finish, exactly as after k_pairs.
 struct WalkFeed { double ray[7][32]; float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };      // 2.75 KB per warp
 #define ARTB_WALK_THREADS 128
+#ifndef ARTB_WALK_BLOCKS
+#define ARTB_WALK_BLOCKS 4
+#endif
 template <bool kBatch>
-__global__ void __launch_bounds__(ARTB_WALK_THREADS, 4)
+__global__ void __launch_bounds__(ARTB_WALK_THREADS, ARTB_WALK_BLOCKS)
 k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
     __shared__ WalkFeed feeds[ARTB_WALK_THREADS / 32];
@@ -659,6 +688,22 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
     }
 }
 
+// constant_medium::hit for one (ray, medium) pair. t_max is the query's own (the candidate's t does not depend on it, and
+// the merge keeps the closest candidate whatever the order: DESIGN section 2); the medium's random number comes from the
+// explicit table (batch hook) or from the Philox stream keyed by (pixel, sample, bounce, medium) — the same key k_finish
+// uses, so both placements of the test draw the same number. Out of line: whole warps run it (class 8 of the tile sort),
+// and its registers must not weigh on the surface tests of k_pairs.
+__device__ __noinline__ bool pair_medium_t(const SceneView* scene, MediumXi xi, uint32_t prim, DRay world, double t_min, double t_max, double* t)
+{
+    // (the scene through a pointer to its copy in global memory and everything else by value: a reference to a kernel
+    // parameter would make every thread of the kernel copy that parameter block into local memory first)
+    const SceneView& s = *scene;
+    return medium_t(s, s.prims[prim], world, t_min, t_max, xi, *t);
+}
+
+#ifndef ARTB_MEDIA_PAIRS_CODE
+#define ARTB_MEDIA_PAIRS_CODE 1       // 0: k_pairs is compiled without the medium class (experiments; media then stay in k_finish)
+#endif
 #ifndef ARTB_PAIRS_THREADS
 #define ARTB_PAIRS_THREADS 64         // small blocks: the three barriers of the tile sort stall fewer warps (measured -4 %)
 #endif
@@ -735,7 +780,7 @@ k_pairs(TraceIO io, SceneView s)
         // points: the primitive tests have many exits, and without them the compiler clones the merge into every exit.
         for (uint32_t base = threadIdx.x & ~31u; base < n_live; base += ARTB_PAIRS_THREADS) {
             const uint32_t i = base + (threadIdx.x & 31u);
-            bool ok = false;
+            bool ok = false, is_medium = false;
             double t = 0.0;
             uint32_t dfs = 0;
             uint32_t ray = 0, prim = 0;
@@ -747,11 +792,28 @@ k_pairs(TraceIO io, SceneView s)
                 const FlatPrim& p = s.prims[prim];
                 dfs = p.dfs_id;
                 DRay q = trace_io_ray<kBatch>(io, ray);
-                if (p.xform) q = to_object_space(s, p.xform, q);
-                ok = surface_t(p, q, io.t_min, io.t_max, t);
+#if ARTB_MEDIA_PAIRS_CODE
+                is_medium = p.type == PRIM_MEDIUM;
+#endif
+                if (is_medium) {                                                       // class 8: whole warps of these
+                    MediumXi xi;
+                    if (kBatch) {
+                        xi.row = io.batch_xi ? io.batch_xi + size_t(ray) * s.n_media : nullptr;
+                        xi.seed = 0; xi.stream = 0; xi.path_lo = ray; xi.path_hi = 0; xi.bounce = 0;
+                    } else {
+                        const PathAux* a = io.aux.at(ray);
+                        xi.row = nullptr; xi.seed = io.seed; xi.stream = io.stream;
+                        xi.path_lo = a->pixel; xi.path_hi = a->sample; xi.bounce = a->depth;
+                    }
+                    ok = pair_medium_t(io.scene_dev, xi, prim, q, io.t_min, io.t_max, &t);
+                }
+                else {
+                    if (p.xform) q = to_object_space(s, p.xform, q);
+                    ok = surface_t(p, q, io.t_min, io.t_max, t);
+                }
             }
             warp_sync();
-            if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs);
+            if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs, s.prim_class, is_medium);
             warp_sync();
         }
         __syncthreads();
@@ -809,7 +871,7 @@ __device__ __forceinline__ void flush_batched_appends(int (*keys)[kThreads], uin
 }
 
 #ifndef ARTB_FINISH_BATCH
-#define ARTB_FINISH_BATCH 4           // iterations per queue reservation in k_finish (1: reserve every iteration)
+#define ARTB_FINISH_BATCH 1           // iterations per queue reservation in k_finish (1: reserve every iteration; 4 and 8 measured the same)
 #endif
 #ifndef ARTB_FINISH_DEFER
 #define ARTB_FINISH_DEFER 0           // deferred queue appends cost k_finish more in spills than the hidden latency gains
@@ -1356,6 +1418,8 @@ struct Renderer::Impl {
     size_t max_shared_nodes = 112 << 10;        // node array up to this size is staged in shared memory by k_traverse
     size_t max_traverse_smem = 112 << 10;       // dynamic shared memory k_traverse may ask for (nodes + traversal stack)
     int bvh_depth = ARTB_STACK_DEPTH;           // levels of 8-wide nodes of the uploaded tree (upload / build_bvh_device)
+    SceneView* view_dev = nullptr;              // copy of the current SceneView in global memory (TraceIO::scene_dev)
+    bool media_pairs = true;                    // constant_media tested by k_pairs (pairs emitted by k_traverse) instead of k_finish
     // device scratch of render_host (grow-only: cudaMalloc costs tens of milliseconds next to a render)
     float* host_accum = nullptr; uint32_t* host_count = nullptr; uint8_t* host_rgb = nullptr;
     size_t host_pixels = 0;
@@ -1395,7 +1459,7 @@ struct Renderer::Impl {
     template <bool kBatch>
     void launch_finish(const SceneView& view, const TraceIO& io, const WaveBuffers& w, const RoundParams& rp, int cur, cudaStream_t st)
     {
-        const bool surf = view.n_global_prims > view.n_global_media, media = view.n_global_media > 0;
+        const bool surf = view.n_global_prims > view.n_global_media, media = view.n_global_media > 0 && !io.media_pairs;
         const unsigned heavy = unsigned(sm_count) * ARTB_FINISH_BLOCKS, light = unsigned(sm_count) * (kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT);
         if (surf && media) k_finish<kBatch, true, true><<<heavy, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
         else if (surf) k_finish<kBatch, true, false><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
@@ -1409,7 +1473,7 @@ struct Renderer::Impl {
                       cudaEvent_t* ev, bool two_phase)
     {
         if (!two_phase) {
-            k_walk<kBatch><<<sm_count * 4, ARTB_WALK_THREADS, 0, st>>>(io, view, w.c, cur);
+            k_walk<kBatch><<<sm_count * ARTB_WALK_BLOCKS, ARTB_WALK_THREADS, 0, st>>>(io, view, w.c, cur);
             if (ev) { CUDA_CHECK(cudaEventRecord(ev[0], st)); CUDA_CHECK(cudaEventRecord(ev[1], st)); }
             launch_finish<kBatch>(view, io, w, rp, cur, st);
             if (ev) CUDA_CHECK(cudaEventRecord(ev[2], st));
@@ -1488,6 +1552,8 @@ void Renderer::init(uint32_t pool_paths)
     CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, false, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
     CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, true, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
 #endif
+    if (const char* e = getenv("ARTB_MEDIA_PAIRS")) impl_->media_pairs = atoi(e) != 0;                 // tuning knob
+    if (!ARTB_MEDIA_PAIRS_CODE) impl_->media_pairs = false;
     if (const char* e = getenv("ARTB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoll(e)));
     cudaStream_t st;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1540,10 +1606,20 @@ void Renderer::release()
     for (cudaEvent_t e : impl_->ev) cudaEventDestroy(e);
     if (impl_->tile_list) cudaFree(impl_->tile_list);
     if (impl_->tile_offsets) cudaFree(impl_->tile_offsets);
+    if (impl_->view_dev) cudaFree(impl_->view_dev);
     if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
     stream_ = nullptr;
     delete impl_;
     impl_ = nullptr;
+}
+
+// the copy of view_ the out-of-line device functions read (TraceIO::scene_dev)
+void Renderer::sync_view()
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (!impl_->view_dev) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&impl_->view_dev), sizeof(SceneView)));
+    CUDA_CHECK(cudaMemcpyAsync(impl_->view_dev, &view_, sizeof(SceneView), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 void Renderer::upload(const FlatScene& fs)
@@ -1596,6 +1672,7 @@ void Renderer::upload(const FlatScene& fs)
     view_ = v;
     scene_bytes_ = bytes;
     has_scene_ = true;
+    sync_view();
     impl_->bvh_depth = fs.bvh_depth;
     max_dfs_id_ = 0;
     for (uint32_t i = 0; i < fs.n_world_prims; ++i) max_dfs_id_ = std::max(max_dfs_id_, fs.prims[i].dfs_id);
@@ -1660,6 +1737,8 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
         io.batch_rays = rays_dev + first * 7;
         io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
         io.batch_out = out_dev + first;
+        io.media_pairs = two_phase && I.media_pairs && view_.n_global_media > 0 ? 1u : 0u;
+        io.scene_dev = I.view_dev;
         I.launch_trace<true>(view_, io, I.wb, RoundParams{}, 0, st, nullptr, two_phase);
         // rays k_finish flagged (pairs did not fit, or more exact ties than the list holds): the one-phase walk
         k_trace_batch<<<I.sm_count * 8, 128, 0, st>>>(view_, io.batch_rays, B.overflow, 0, B.ctr + 3, B.overflow_total, t_min, t_max,
@@ -1865,6 +1944,7 @@ void Renderer::build_bvh_device(int max_leaf_prims, BvhBuildStats* stats)
         view_.nodes = nodes;                 // the previous node array stays in scene_allocs until the next upload
         view_.n_nodes = S.n_nodes;
         impl_->bvh_depth = S.depth;
+        sync_view();
     } catch (...) {
         for (void* p : bag) cudaFree(p);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -2031,6 +2111,9 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
                     io.t_min = 0.001; io.t_max = INFINITY;
                     io.rays = w.rays; io.aux = w.aux;
+                    io.seed = rp.seed; io.stream = rp.stream;
+                    io.media_pairs = two_phase && I.media_pairs && view_.n_global_media > 0 ? 1u : 0u;
+                    io.scene_dev = I.view_dev;
                     I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr, two_phase);
                     // overflow pass: only the pair kernels can flag rays (full regions, more exact ties than the list holds)
                     if (two_phase) k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);

@@ -120,6 +120,7 @@ public:
 private:
     void init(uint32_t pool_paths);
     void release();
+    void sync_view();
     struct Impl;
     Impl* impl_;
     int device_;

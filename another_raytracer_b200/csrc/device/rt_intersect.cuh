@@ -220,20 +220,6 @@ ARTB_HD bool medium_t(const SceneView& s, const FlatPrim& p, const DRay& world, 
     // ... and before the boundary is even intersected: the clamped interval lies within [max(t_min, 0), t_max], and
     // subtraction and multiplication round monotonically, so (t_max - max(t_min, 0)) * |d| bounds it from above
     if (hit_distance_lo > (t_max - (t_min > 0 ? t_min : 0.0)) * ray_length) return false;
-    // ... and for a ray that escapes (t_max = inf: the bound above says nothing) through a spherical boundary: the part of
-    // the ray inside a sphere of radius R, seen from an origin at distance D from its centre, is never longer than D + R
-    // (origin inside: the far side is at most D + R away; outside: a chord is at most 2R < D + R), and translate / rotate_y
-    // are isometries, so D can be measured in world space against the transformed centre — or, as here, only for boundaries
-    // without a transform. Float arithmetic with a 1e-5 relative margin, far above its rounding errors.
-    {
-        const FlatPrim& b = s.prims[first];
-        if (count == 1 && b.type == PRIM_SPHERE && b.xform == 0u) {
-            const d3 oc = world.o - ld3(b.g);
-            const float d2 = float(length_squared(oc));
-            const float reach = (sqrtf(d2) + fabsf(float(b.g[3]))) * 1.00001f + 1e-30f;
-            if (hit_distance_lo > double(reach)) return false;
-        }
-    }
     double t1, t2;
     if (!medium_interval(s, first, count, world, t1, t2)) return false;
     if (t1 < t_min) t1 = t_min;
@@ -385,7 +371,7 @@ ARTB_HD BoxRay make_box_ray(const TravRay& t)
 
 // Conservative slab test against an explicit float box (used for the media's world boxes). Error budget as in
 // node8_hits below: planes are exact floats, so the only errors are the roundings of inv, c and the FMA.
-ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best)
+ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best, float* t_enter = nullptr)
 {
     float tn = t_min, tf = t_best;
 #pragma unroll
@@ -397,6 +383,7 @@ ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t
         tn = fmaxf(tn, n - pad);
         tf = fminf(tf, f + pad);
     }
+    if (t_enter) *t_enter = tn;          // a lower bound of the parameter of anything the ray meets inside the box
     return tn <= tf;
 }
 
