@@ -55,13 +55,12 @@ enum : uint32_t { TEX_SOLID = ARTB_TEX_SOLID, TEX_CHECKER = ARTB_TEX_CHECKER, TE
 // device-side view (all pointers are device pointers)
 // Code path a primitive takes in the double-precision test: k_pairs sorts each tile of pairs by it so that the lanes of
 // a warp run the same test (sphere / moving sphere / rect / triangle, each without or with a transform chain).
-#define ARTB_PRIM_CLASSES 9           // 0-7: surfaces (below); 8: constant_medium pairs (k_traverse emits one per medium box a ray enters)
+#define ARTB_PRIM_CLASSES 8
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
 inline uint32_t prim_class_of(uint32_t type, uint32_t xform)
 {
-    if (type == PRIM_MEDIUM) return 8u;
     const uint32_t path = type == PRIM_SPHERE ? 0u : type == PRIM_MSPHERE ? 1u : type == PRIM_TRIANGLE ? 3u : 2u;
     return path * 2u + (xform ? 1u : 0u);
 }
@@ -84,6 +83,11 @@ struct SceneView {
     uint32_t one_bits;                // 0x3f800000 as a RUNTIME value: the node test wants it in a register next to immediate
                                       // PRMT selectors; as a literal ptxas re-materialises it before every PRMT (rt_intersect.cuh)
     double background[3];
+    // This view in memory the out-of-line device functions can point at (tie_replaces, medium_interval_general,
+    // replay_ties): the device copy in global memory (Renderer::sync_view), the object itself on the host. They take this
+    // pointer and their other arguments by value — a C++ reference to a kernel parameter would make every thread of the
+    // kernel copy the whole parameter block into local memory at start-up (a 256-480 byte stack frame per thread).
+    const SceneView* self;
 };
 
 struct CameraParams {     // camera.h:49-56 + engine.h:62-63

@@ -282,10 +282,6 @@ struct TraceIO {
     double t_min, t_max;
     Strided<PathRay> rays;            // wave mode: the path pool
     Strided<PathAux> aux;
-    uint32_t seed, stream;            // wave mode: Philox key of the render (the media's draws: MediumXi)
-    const SceneView* scene_dev;       // the SceneView in global memory (for out-of-line device functions)
-    uint32_t media_pairs;             // 1: k_traverse emits a (ray, medium) pair per medium box the ray enters and k_pairs
-                                      // runs constant_medium::hit; 0: k_finish tests the media ray by ray
     const double* batch_rays;         // batch mode: n * 7 doubles
     const double* batch_xi;           // batch mode: n * n_media explicit medium draws, or nullptr
     HitRecordOut* batch_out;
@@ -346,12 +342,9 @@ __device__ __forceinline__ bool cas_hit(PathHit* h, unsigned long long& cur_lo, 
 // million rays. The record keeps the later leaf and gets ARTB_HIT_TIED set, the other leaf goes to the ray's tie list;
 // k_finish — which has the ray — replays the tied leaves in the reference's order.
 #define ARTB_HIT_TIED 0x80000000u     // bit 31 of PathHit::dfs
-// A constant_medium on either side of an exact tie: the later one in the reference's order wins (every leaf, a medium
-// included, accepts t == t_max: constant_medium.h:52-69 clamps its interval to t_max and keeps a scatter point AT the end);
-// the reference-bvh-box subtlety of surface ties (tie_later_wins) does not arise: media sit in plain lists. Decided here.
 template <bool kBatch>
 __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, unsigned long long cur_lo, unsigned long long cur_hi,
-                                          double t, uint32_t prim, uint32_t dfs, const uint8_t* prim_class = nullptr, bool is_medium = false)
+                                          double t, uint32_t prim, uint32_t dfs)
 {
     PathHit* h = io.hits.at(ray_id);
     for (;;) {
@@ -365,14 +358,9 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
             if (t > cur_t) return;
             if (t == cur_t) {
                 const uint32_t cur_dfs = uint32_t(cur_hi >> 32);
-                if (prim_class && (is_medium || prim_class[cur_prim] == 8u)) {
-                    if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) return;          // the record's leaf comes later: it stays
-                    new_hi |= cur_hi & ((unsigned long long)ARTB_HIT_TIED << 32);   // surface ties already noted stay noted
-                } else {
-                    if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
-                    else other = uint32_t(cur_prim);
-                    new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
-                }
+                if ((cur_dfs & ~ARTB_HIT_TIED) >= dfs) { new_lo = cur_lo; new_hi = cur_hi; other = prim; }
+                else other = uint32_t(cur_prim);
+                new_hi |= (unsigned long long)ARTB_HIT_TIED << 32;
             }
         } else if (!(t <= cur_t)) return;
         if (cas_hit(h, cur_lo, cur_hi, new_lo, new_hi)) {
@@ -498,20 +486,6 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
                     feed.id[lane] = rid;
                     store_hit(io.hits.at(rid), io.t_max, -1, 0u);
                     io.ties.at(rid)->n = 0u;
-                    if (io.media_pairs) {
-                        // one pair per constant_medium whose world box the ray enters (here, with all lanes of the warp
-                        // busy): k_pairs runs constant_medium::hit on them next to the surface tests
-                        for (uint32_t mi = s.n_global_prims - s.n_global_media; mi < s.n_global_prims; ++mi) {
-                            const FlatPrim& mp = s.prims[mi];
-                            const float lo[3] = { d2f_rd(mp.g[4]), d2f_rd(mp.g[5]), d2f_rd(mp.g[6]) };
-                            const float hi[3] = { d2f_ru(mp.g[7]), d2f_ru(mp.g[8]), d2f_ru(mp.g[9]) };
-                            float tn = 0.f;
-                            if (!slab_box(lo, hi, b, t_min_f, t_max_f, &tn)) continue;
-                            const uint32_t pos = atomicAdd(&s_pairs, 1u);
-                            if (pos < cap) region[pos] = pack_pair(rid, mi, tn);
-                            else mark_overflow(io.hits.at(rid));       // region full: the one-phase pass traces this ray
-                        }
-                    }
                 }
                 __syncwarp();
                 feed_count = got;
@@ -688,22 +662,6 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
     }
 }
 
-// constant_medium::hit for one (ray, medium) pair. t_max is the query's own (the candidate's t does not depend on it, and
-// the merge keeps the closest candidate whatever the order: DESIGN section 2); the medium's random number comes from the
-// explicit table (batch hook) or from the Philox stream keyed by (pixel, sample, bounce, medium) — the same key k_finish
-// uses, so both placements of the test draw the same number. Out of line: whole warps run it (class 8 of the tile sort),
-// and its registers must not weigh on the surface tests of k_pairs.
-__device__ __noinline__ bool pair_medium_t(const SceneView* scene, MediumXi xi, uint32_t prim, DRay world, double t_min, double t_max, double* t)
-{
-    // (the scene through a pointer to its copy in global memory and everything else by value: a reference to a kernel
-    // parameter would make every thread of the kernel copy that parameter block into local memory first)
-    const SceneView& s = *scene;
-    return medium_t(s, s.prims[prim], world, t_min, t_max, xi, *t);
-}
-
-#ifndef ARTB_MEDIA_PAIRS_CODE
-#define ARTB_MEDIA_PAIRS_CODE 1       // 0: k_pairs is compiled without the medium class (experiments; media then stay in k_finish)
-#endif
 #ifndef ARTB_PAIRS_THREADS
 #define ARTB_PAIRS_THREADS 64         // small blocks: the three barriers of the tile sort stall fewer warps (measured -4 %)
 #endif
@@ -780,7 +738,7 @@ k_pairs(TraceIO io, SceneView s)
         // points: the primitive tests have many exits, and without them the compiler clones the merge into every exit.
         for (uint32_t base = threadIdx.x & ~31u; base < n_live; base += ARTB_PAIRS_THREADS) {
             const uint32_t i = base + (threadIdx.x & 31u);
-            bool ok = false, is_medium = false;
+            bool ok = false;
             double t = 0.0;
             uint32_t dfs = 0;
             uint32_t ray = 0, prim = 0;
@@ -792,28 +750,11 @@ k_pairs(TraceIO io, SceneView s)
                 const FlatPrim& p = s.prims[prim];
                 dfs = p.dfs_id;
                 DRay q = trace_io_ray<kBatch>(io, ray);
-#if ARTB_MEDIA_PAIRS_CODE
-                is_medium = p.type == PRIM_MEDIUM;
-#endif
-                if (is_medium) {                                                       // class 8: whole warps of these
-                    MediumXi xi;
-                    if (kBatch) {
-                        xi.row = io.batch_xi ? io.batch_xi + size_t(ray) * s.n_media : nullptr;
-                        xi.seed = 0; xi.stream = 0; xi.path_lo = ray; xi.path_hi = 0; xi.bounce = 0;
-                    } else {
-                        const PathAux* a = io.aux.at(ray);
-                        xi.row = nullptr; xi.seed = io.seed; xi.stream = io.stream;
-                        xi.path_lo = a->pixel; xi.path_hi = a->sample; xi.bounce = a->depth;
-                    }
-                    ok = pair_medium_t(io.scene_dev, xi, prim, q, io.t_min, io.t_max, &t);
-                }
-                else {
-                    if (p.xform) q = to_object_space(s, p.xform, q);
-                    ok = surface_t(p, q, io.t_min, io.t_max, t);
-                }
+                if (p.xform) q = to_object_space(s, p.xform, q);
+                ok = surface_t(p, q, io.t_min, io.t_max, t);
             }
             warp_sync();
-            if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs, s.prim_class, is_medium);
+            if (ok && t == t) merge_hit<kBatch>(io, ray, cur_lo, cur_hi, t, prim, dfs);
             warp_sync();
         }
         __syncthreads();
@@ -822,9 +763,12 @@ k_pairs(TraceIO io, SceneView s)
 
 // Several leaves report the same t: test them again one by one in the reference's depth-first order, as
 // hittable_list::hit / bvh_node::hit would (test_surface applies the exact rule, hit_replaces). Rare: out of line.
-__device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie, uint32_t n_tied, uint32_t record_prim, const DRay& r,
-                                         double t_min, double t_max, ClosestHit& best)
+__device__ __noinline__ ClosestHit replay_ties(const SceneView* scene, const PathTie* tie, uint32_t n_tied, uint32_t record_prim, DRay r,
+                                               double t_min, double t_max)
 {
+    // (scene through its copy in global memory, the ray by value: a reference to a kernel parameter would make every
+    // thread of the calling kernel copy the parameter block to local memory)
+    const SceneView& s = *scene;
     uint32_t cand[4];
     for (uint32_t k = 0; k < n_tied; ++k) cand[k] = tie->prim[k];
     cand[n_tied] = record_prim;
@@ -832,8 +776,10 @@ __device__ __noinline__ void replay_ties(const SceneView& s, const PathTie* tie,
         for (uint32_t b = a; b > 0 && s.prims[cand[b - 1]].dfs_id > s.prims[cand[b]].dfs_id; --b) {
             const uint32_t tmp = cand[b]; cand[b] = cand[b - 1]; cand[b - 1] = tmp;
         }
+    ClosestHit best;
     best.t = t_max; best.prim = -1; best.dfs = 0;
     for (uint32_t k = 0; k <= n_tied; ++k) test_surface(s, cand[k], r, t_min, best);
+    return best;
 }
 
 // Queue appends of SEVERAL loop iterations with one atomic per queue: a warp parks the (queue, slot) of each of its last
@@ -884,14 +830,17 @@ __device__ __forceinline__ void flush_batched_appends(int (*keys)[kThreads], uin
 #endif
 // kSurf / kMedia: whether the scene HAS global surfaces / global media. The kernel is compiled once per combination so that
 // a scene without media (Cornell box, the sphere scenes) or without global surfaces (final scene, the meshes) does not carry
-// the code it never runs (Cornell box: -23 % on this kernel). Measured with the register budget varied per variant
-// (profiles/r02_finish_variants.txt): spills cost every variant more than the extra resident warps give back, so all of
-// them get the 168 registers of 3 blocks per SM.
+// the code it never runs (Cornell box: -23 % on this kernel), and the variant with neither reads only the 16-byte hit
+// records. Register budgets measured per variant (profiles/r02_finish_variants.txt): spills cost every variant more than the
+// extra resident warps give back — 3 blocks (168 registers) where media are tested, 4 blocks (128, no spills) elsewhere.
 #ifndef ARTB_FINISH_BLOCKS_LIGHT
-#define ARTB_FINISH_BLOCKS_LIGHT ARTB_FINISH_BLOCKS
+#define ARTB_FINISH_BLOCKS_LIGHT 4
+#endif
+#ifndef ARTB_FINISH_BLOCKS_BIN
+#define ARTB_FINISH_BLOCKS_BIN 4
 #endif
 template <bool kBatch, bool kSurf, bool kMedia>
-__global__ void __launch_bounds__(ARTB_FINISH_THREADS, (kSurf && kMedia) || kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT)
+__global__ void __launch_bounds__(ARTB_FINISH_THREADS, kBatch || kMedia ? ARTB_FINISH_BLOCKS : kSurf ? ARTB_FINISH_BLOCKS_LIGHT : ARTB_FINISH_BLOCKS_BIN)
 k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 {
     const uint32_t n = *io.n_ptr;
@@ -924,18 +873,24 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
         r.o = mk3(0, 0, 0); r.d = mk3(1, 0, 0); r.tm = 0;
         PathAux a;
         a.thr[0] = a.thr[1] = a.thr[2] = 0.f; a.pixel = a.sample = a.rng_block = a.depth = a.pad = 0;
+        // A scene without global surfaces and media (or with its media tested by k_pairs) needs only the 16-byte hit
+        // record here; the ray is read for the rare exact tie, the bookkeeping record for a miss. Everything else reads
+        // all three at once.
+        constexpr bool kNeedRay = kSurf || kMedia || kBatch;
         if (valid) {
             ph = load_hit(io.hits.at(id));
-            r = trace_io_ray<kBatch>(io, id);
-            if (!kBatch) load_aux(io.aux.at(id), a);
+            if (kNeedRay) r = trace_io_ray<kBatch>(io, id);
+            if (!kBatch && kMedia) load_aux(io.aux.at(id), a);
         }
         if (next_idx < n) {
             prefetch_l1(io.hits.at(next_id));
             if (kBatch) prefetch_l1(io.batch_rays + size_t(next_id) * 7);
-            else { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
+            else if (kNeedRay) { prefetch_l1(io.rays.at(next_id)); prefetch_l1(io.aux.at(next_id)); }
         }
         // flagged by k_traverse (pairs did not fit), or more leaves tied than the list holds: the one-phase pass traces the ray
         const bool tied = valid && ph.prim >= 0 && (ph.dfs & ARTB_HIT_TIED) != 0u;
+        if (!kNeedRay && tied) r = trace_io_ray<kBatch>(io, id);
+        if (!kBatch && !kMedia && valid && ph.prim < 0 && ph.prim != ARTB_HIT_OVERFLOW) load_aux(io.aux.at(id), a);     // a miss (no global surface can turn it into a hit)
         uint32_t n_tied = 0;
         if (tied) n_tied = io.ties.at(id)->n;
         const bool overflow = ph.prim == ARTB_HIT_OVERFLOW || n_tied > 3u;
@@ -945,7 +900,7 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
         if (live) {
             ClosestHit best;
             best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs & ~ARTB_HIT_TIED;
-            if (tied) replay_ties(s, io.ties.at(id), n_tied, uint32_t(ph.prim), r, io.t_min, io.t_max, best);
+            if (tied) best = replay_ties(s.self, io.ties.at(id), n_tied, uint32_t(ph.prim), r, io.t_min, io.t_max);
             if (kSurf) for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
             if (kMedia && s.n_global_media) {
                 MediumXi xi;
@@ -1419,7 +1374,6 @@ struct Renderer::Impl {
     size_t max_traverse_smem = 112 << 10;       // dynamic shared memory k_traverse may ask for (nodes + traversal stack)
     int bvh_depth = ARTB_STACK_DEPTH;           // levels of 8-wide nodes of the uploaded tree (upload / build_bvh_device)
     SceneView* view_dev = nullptr;              // copy of the current SceneView in global memory (TraceIO::scene_dev)
-    bool media_pairs = true;                    // constant_media tested by k_pairs (pairs emitted by k_traverse) instead of k_finish
     // device scratch of render_host (grow-only: cudaMalloc costs tens of milliseconds next to a render)
     float* host_accum = nullptr; uint32_t* host_count = nullptr; uint8_t* host_rgb = nullptr;
     size_t host_pixels = 0;
@@ -1459,12 +1413,14 @@ struct Renderer::Impl {
     template <bool kBatch>
     void launch_finish(const SceneView& view, const TraceIO& io, const WaveBuffers& w, const RoundParams& rp, int cur, cudaStream_t st)
     {
-        const bool surf = view.n_global_prims > view.n_global_media, media = view.n_global_media > 0 && !io.media_pairs;
-        const unsigned heavy = unsigned(sm_count) * ARTB_FINISH_BLOCKS, light = unsigned(sm_count) * (kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT);
+        const bool surf = view.n_global_prims > view.n_global_media, media = view.n_global_media > 0;
+        const unsigned heavy = unsigned(sm_count) * ARTB_FINISH_BLOCKS;
+        const unsigned light = unsigned(sm_count) * (kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_LIGHT);
+        const unsigned bin = unsigned(sm_count) * (kBatch ? ARTB_FINISH_BLOCKS : ARTB_FINISH_BLOCKS_BIN);
         if (surf && media) k_finish<kBatch, true, true><<<heavy, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
         else if (surf) k_finish<kBatch, true, false><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
-        else if (media) k_finish<kBatch, false, true><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
-        else k_finish<kBatch, false, false><<<light, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        else if (media) k_finish<kBatch, false, true><<<heavy, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
+        else k_finish<kBatch, false, false><<<bin, ARTB_FINISH_THREADS, 0, st>>>(io, view, w, rp, cur);
     }
     // two_phase: k_traverse + k_pairs + k_finish; otherwise the pruned walk k_walk + k_finish (trees beyond shared memory).
     // ev (optional): three events recorded after the tree kernel, after k_pairs (at once in walk mode) and after k_finish.
@@ -1552,8 +1508,6 @@ void Renderer::init(uint32_t pool_paths)
     CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, false, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
     CUDA_CHECK(cudaFuncSetAttribute(k_traverse<true, true, ARTB_SMEM_STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(impl_->max_traverse_smem)));
 #endif
-    if (const char* e = getenv("ARTB_MEDIA_PAIRS")) impl_->media_pairs = atoi(e) != 0;                 // tuning knob
-    if (!ARTB_MEDIA_PAIRS_CODE) impl_->media_pairs = false;
     if (const char* e = getenv("ARTB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoll(e)));
     cudaStream_t st;
     CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -1618,6 +1572,7 @@ void Renderer::sync_view()
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (!impl_->view_dev) CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&impl_->view_dev), sizeof(SceneView)));
+    view_.self = impl_->view_dev;
     CUDA_CHECK(cudaMemcpyAsync(impl_->view_dev, &view_, sizeof(SceneView), cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
@@ -1737,8 +1692,6 @@ float Renderer::trace_batch_device(const double* rays_dev, uint64_t n, double t_
         io.batch_rays = rays_dev + first * 7;
         io.batch_xi = xi_dev ? xi_dev + first * view_.n_media : nullptr;
         io.batch_out = out_dev + first;
-        io.media_pairs = two_phase && I.media_pairs && view_.n_global_media > 0 ? 1u : 0u;
-        io.scene_dev = I.view_dev;
         I.launch_trace<true>(view_, io, I.wb, RoundParams{}, 0, st, nullptr, two_phase);
         // rays k_finish flagged (pairs did not fit, or more exact ties than the list holds): the one-phase walk
         k_trace_batch<<<I.sm_count * 8, 128, 0, st>>>(view_, io.batch_rays, B.overflow, 0, B.ctr + 3, B.overflow_total, t_min, t_max,
@@ -2111,10 +2064,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
                     io.q_overflow = w.q_overflow; io.n_overflow = &w.c->n_overflow;
                     io.t_min = 0.001; io.t_max = INFINITY;
                     io.rays = w.rays; io.aux = w.aux;
-                    io.seed = rp.seed; io.stream = rp.stream;
-                    io.media_pairs = two_phase && I.media_pairs && view_.n_global_media > 0 ? 1u : 0u;
-                    io.scene_dev = I.view_dev;
-                    I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr, two_phase);
+                                I.launch_trace<false>(view_, io, w, rp, cur, st, profile ? &I.ev[5 * pairs_used + 1] : nullptr, two_phase);
                     // overflow pass: only the pair kernels can flag rays (full regions, more exact ties than the list holds)
                     if (two_phase) k_extend<<<I.sm_count * 4, ARTB_EXTEND_THREADS, 0, st>>>(w, view_, rp, cur, 0);
                     S.launches += two_phase ? 5 : 3;

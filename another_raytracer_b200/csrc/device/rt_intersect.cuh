@@ -163,11 +163,12 @@ struct MediumXi {
 
 // The two boundary queries of a medium (constant_medium.h:44-47): rec1 = boundary.hit(-inf, inf),
 // rec2 = boundary.hit(rec1.t + 0.0001, inf).
-ARTB_HD_NOINLINE bool medium_interval_general(const SceneView& s, uint32_t first, uint32_t count, const DRay& world,
-                                              double& t1, double& t2)
+ARTB_HD_NOINLINE bool medium_interval_general(const SceneView* scene, uint32_t first, uint32_t count, DRay world,
+                                              double* t1, double* t2)
 {
-    if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, t1)) return false;
-    return boundary_t(s, first, count, world, t1 + 0.0001, INFINITY, t2);
+    const SceneView& s = *scene;
+    if (!boundary_t(s, first, count, world, -INFINITY, INFINITY, *t1)) return false;
+    return boundary_t(s, first, count, world, *t1 + 0.0001, INFINITY, *t2);
 }
 
 ARTB_HD bool medium_interval(const SceneView& s, uint32_t first, uint32_t count, const DRay& world, double& t1, double& t2)
@@ -194,7 +195,7 @@ ARTB_HD bool medium_interval(const SceneView& s, uint32_t first, uint32_t count,
             return true;
         }
     }
-    return medium_interval_general(s, first, count, world, t1, t2);
+    return medium_interval_general(s.self, first, count, world, &t1, &t2);
 }
 
 // log(u) behind a call: the compiler must not start the (long) double-precision logarithm before the float test
@@ -279,9 +280,10 @@ ARTB_HD bool tie_later_wins(const SceneView& s, const DRay& world, double t_min,
 // The merge rule, i.e. what hittable_list::hit / bvh_node::hit do by narrowing t_max (hittable_list.cpp:11-15,
 // bvh.cpp:48-49): a candidate replaces the best iff it is closer; at equal t the leaf that comes later in the
 // reference's depth-first order wins, provided the reference would have visited it (tie_later_wins).
-ARTB_HD_NOINLINE bool tie_replaces(const SceneView& s, const DRay& world, double t_min, double t, uint32_t prim, uint32_t dfs,
+ARTB_HD_NOINLINE bool tie_replaces(const SceneView* scene, DRay world, double t_min, double t, uint32_t prim, uint32_t dfs,
                                    uint32_t best_prim, uint32_t best_dfs)
 {
+    const SceneView& s = *scene;
     if (dfs > best_dfs) return tie_later_wins(s, world, t_min, t, best_prim, prim);
     return !tie_later_wins(s, world, t_min, t, prim, best_prim);
 }
@@ -291,7 +293,7 @@ ARTB_HD bool hit_replaces(const SceneView& s, const DRay& world, double t_min, d
 {
     if (t < best_t || best_prim < 0) return t <= best_t;
     if (t != best_t) return false;
-    return tie_replaces(s, world, t_min, t, prim, dfs, uint32_t(best_prim), best_dfs);       // rare, out of line
+    return tie_replaces(s.self, world, t_min, t, prim, dfs, uint32_t(best_prim), best_dfs);  // rare, out of line
 }
 
 // ---- closest hit ----------------------------------------------------------------------------------
@@ -371,7 +373,7 @@ ARTB_HD BoxRay make_box_ray(const TravRay& t)
 
 // Conservative slab test against an explicit float box (used for the media's world boxes). Error budget as in
 // node8_hits below: planes are exact floats, so the only errors are the roundings of inv, c and the FMA.
-ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best, float* t_enter = nullptr)
+ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t_min, float t_best)
 {
     float tn = t_min, tf = t_best;
 #pragma unroll
@@ -383,7 +385,6 @@ ARTB_HD bool slab_box(const float* lo, const float* hi, const BoxRay& r, float t
         tn = fmaxf(tn, n - pad);
         tf = fminf(tf, f + pad);
     }
-    if (t_enter) *t_enter = tn;          // a lower bound of the parameter of anything the ray meets inside the box
     return tn <= tf;
 }
 

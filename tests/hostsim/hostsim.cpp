@@ -41,6 +41,7 @@ int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, doub
     s.one_bits = 0x3f800000u;
     for (uint32_t i = 0; i < s.n_global_prims; ++i) s.n_global_media += s.prims[i].type == PRIM_MEDIUM ? 1u : 0u;
     for (int k = 0; k < 3; ++k) s.background[k] = f->background[k];
+    s.self = &s;                      // the out-of-line helpers of rt_intersect.cuh reach the view through this pointer
 
     TraversalStats st{};
     for (uint64_t i = 0; i < n; ++i) {
