@@ -349,10 +349,13 @@ def run_cuda_arm(args, wl):
                     D.reduce_frames(step_accum)
                     if rank == 0:
                         ctx.resolve_device(step_accum.data_ptr(), None, W * H, S * world, rgb.data_ptr())
-                        host_rgb.copy_(rgb, non_blocking=True)
-                        host_acc.copy_(step_accum, non_blocking=True)
-                        d2h += host_rgb.numel() + host_acc.numel() * 4
-                    lib_stream.synchronize()
+                lib_stream.synchronize()
+                if rank == 0:
+                    # (copies on torch's own stream: a pinned block remembers the stream it was last used on, and the
+                    # library's stream is gone by the time torch releases its host cache at exit)
+                    host_rgb.copy_(rgb)
+                    host_acc.copy_(step_accum)
+                    d2h += host_rgb.numel() + host_acc.numel() * 4
             e_samples += st["samples"]
             if os.environ.get("ARTB_BENCH_DEBUG"):
                 print(f"e2e step {k}: wall so far {time.perf_counter() - te:.3f} s, device {st['elapsed_ms']:.1f} ms", file=sys.stderr)
@@ -422,7 +425,11 @@ def run_cuda_arm(args, wl):
             "image_checksum": checksum,
         }
         print(json.dumps(line), flush=True)
+    # torch objects that were used on the library's stream are released before the context that owns that stream
+    torch.cuda.synchronize()
+    del ev, lib_stream
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     ctx.close()
     return 0
