@@ -1094,9 +1094,6 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
 #ifndef ARTB_SHADE_BLOCKS
 #define ARTB_SHADE_BLOCKS 4
 #endif
-#ifndef ARTB_SHADE_STAGE
-#define ARTB_SHADE_STAGE 1            // path records staged through shared memory with cp.async one iteration ahead
-#endif
 #ifndef ARTB_SHADE_BATCH
 #define ARTB_SHADE_BATCH 4            // iterations per queue reservation (1: the deferred per-iteration append)
 #endif
@@ -1171,37 +1168,9 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
         n_parked = 0;
     };
 #endif
-#if ARTB_SHADE_STAGE
-    // Path records staged through SHARED memory with cp.async, one iteration ahead: the 112 bytes (ray | bookkeeping | hit)
-    // this lane shades in iteration k+1 are copied — asynchronously, holding no register — while it shades iteration k, so
-    // the record is read from shared memory instead of waiting for DRAM; the slot id the copy needs is itself loaded one
-    // more iteration ahead. Layout [stage][16-byte chunk][thread]: a warp's reads of one chunk are 512 contiguous bytes.
-    __shared__ uint4 s_rec[2][7][128];
-    auto stage_copy = [&](int stage, uint32_t sl) {
-        const char* src = w.rays.base + size_t(sl) * w.rays.stride;
-#pragma unroll
-        for (int ch = 0; ch < 7; ++ch) {
-            const uint32_t dst = uint32_t(__cvta_generic_to_shared(&s_rec[stage][ch][threadIdx.x]));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src + ch * 16) : "memory");
-        }
-    };
-    int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
-    uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
-    if (valid && m != Q_REGEN) stage_copy(0, slot);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    int stage = 0;
-#endif
     for (; wi < start[Q_OUT_COUNT]; wi += n_warps) {
-#if ARTB_SHADE_STAGE
-        int far_m = 0; uint32_t far_i = 0; bool far_valid = false;
-        const uint32_t far_slot = locate(wi + 2u * n_warps, far_m, far_i, far_valid);
-        if (next_valid && next_m != Q_REGEN) stage_copy(stage ^ 1, next_slot);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");        // everything but the copy just queued has landed
-#else
         int next_m = 0; uint32_t next_i = 0; bool next_valid = false;
         const uint32_t next_slot = locate(wi + n_warps, next_m, next_i, next_valid);
-#endif
         int key = -1;                       // 0: a ray for the next wave, 1: slot is free
         if (m == Q_REGEN) {
             if (valid) {
@@ -1228,21 +1197,6 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
                 }
             }
         } else if (valid) {
-#if ARTB_SHADE_STAGE
-            DRay r;
-            PathAux a;
-            PathHit ph;
-            {
-                const uint4 c0 = s_rec[stage][0][threadIdx.x], c1 = s_rec[stage][1][threadIdx.x], c2 = s_rec[stage][2][threadIdx.x],
-                            c3 = s_rec[stage][3][threadIdx.x];
-                const double2 d0 = *reinterpret_cast<const double2*>(&c0), d1 = *reinterpret_cast<const double2*>(&c1),
-                              d2 = *reinterpret_cast<const double2*>(&c2), d3v = *reinterpret_cast<const double2*>(&c3);
-                r.o = mk3(d0.x, d0.y, d1.x); r.d = mk3(d1.y, d2.x, d2.y); r.tm = d3v.x;
-                *reinterpret_cast<uint4*>(&a) = s_rec[stage][4][threadIdx.x];
-                *(reinterpret_cast<uint4*>(&a) + 1) = s_rec[stage][5][threadIdx.x];
-                *reinterpret_cast<uint4*>(&ph) = s_rec[stage][6][threadIdx.x];
-            }
-#else
             const DRay r = load_ray(w.rays.at(slot));
             PathAux a;
             load_aux(w.aux.at(slot), a);
@@ -1250,7 +1204,6 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
             if (next_valid && next_m != Q_REGEN) {
                 prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
             }
-#endif
             const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
             const FlatMaterial& mat = s.materials[h.material];
             key = 1;
@@ -1283,14 +1236,7 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
                        key == 1 ? w.q_regen[cur ^ 1] : w.q_extend[cur ^ 1], slot, lane);
 #endif
         m = next_m; i = next_i; valid = next_valid; slot = next_slot;
-#if ARTB_SHADE_STAGE
-        next_m = far_m; next_i = far_i; next_valid = far_valid; next_slot = far_slot;
-        stage ^= 1;
-#endif
     }
-#if ARTB_SHADE_STAGE
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#endif
 #if ARTB_SHADE_BATCH > 1
     if (n_parked) flush();
 #endif
