@@ -496,8 +496,8 @@ ARTB_HD void trav_begin(Traversal& tv, double t_max, bool has_tree)
 #define ARTB_PRIM_VOTE_DEN 2
 #endif
 
-template <class NodePtr>
-ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Traversal& tv, uint2* stack, const DRay& ray,
+template <class NodePtr, class Stack>
+ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Traversal& tv, Stack& stack, const DRay& ray,
                             const BoxRay& br, double t_min, float t_min_f, TraversalStats* stats)
 {
     if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
