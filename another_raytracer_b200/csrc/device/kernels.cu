@@ -595,13 +595,7 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
     WalkFeed& feed = feeds[threadIdx.x >> 5];
     uint32_t feed_count = 0;          // warp-uniform
     bool more = true;                 // warp-uniform
-    // the traversal stack in shared memory, [entry][thread] (32 KB per block): as a lane-private array it lived in local
-    // memory, and its pops were 6 % of this kernel's stall samples
-    __shared__ uint2 s_stack[ARTB_STACK_DEPTH][ARTB_WALK_THREADS];
-    struct WalkStack {
-        uint2* base;
-        __device__ __forceinline__ uint2& operator[](int i) { return base[uint32_t(i) * ARTB_WALK_THREADS]; }
-    } stack{ &s_stack[0][threadIdx.x] };
+    uint2 stack[ARTB_STACK_DEPTH];      // (in shared memory, [entry][thread]: measured 2 % slower)
     Traversal tv;
     trav_begin(tv, io.t_max, false);
     tv.alive = false;
