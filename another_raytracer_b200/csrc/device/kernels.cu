@@ -2220,6 +2220,13 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     if (stats) *stats = S;
 }
 
+// joins whatever was started, also when starting the next thread throws (a joinable std::thread must not be destroyed)
+struct ThreadGroup {
+    std::vector<std::thread> threads;
+    ~ThreadGroup() { join(); }
+    void join() { for (auto& t : threads) if (t.joinable()) t.join(); }
+};
+
 // ---- several GPUs in one process: the exchange -----------------------------------------------------------------------
 // dst += the frames of up to 7 peers, read in place over NVLink (peer access) — the exchange of engine_mode::
 // parallel_images (engine.h:424-440: the four workers' float frames summed pixel by pixel) fused with nothing else because
@@ -2328,9 +2335,9 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
                 std::vector<std::string> errors(static_cast<size_t>(n));
                 std::vector<float*> pacc(static_cast<size_t>(n_peers), nullptr);
                 std::vector<uint32_t*> pcnt(static_cast<size_t>(n_peers), nullptr);
-                std::vector<std::thread> threads;
+                ThreadGroup workers;
                 for (int k = 0; k < n; ++k) {
-                    threads.emplace_back([&, k]() {
+                    workers.threads.emplace_back([&, k]() {
                         try {
                             const uint32_t b = uint32_t(uint64_t(n_px) * uint64_t(k) / uint64_t(n));
                             const uint32_t e = uint32_t(uint64_t(n_px) * uint64_t(k + 1) / uint64_t(n));
@@ -2353,10 +2360,12 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
                             else CUDA_CHECK(cudaMemset(pacc[size_t(k - 1)], 0, n_pixels * 3 * sizeof(float)));
                         } catch (const std::exception& ex) {
                             errors[size_t(k)] = ex.what();
+                        } catch (...) {
+                            errors[size_t(k)] = "unknown error";
                         }
                     });
                 }
-                for (auto& t : threads) t.join();
+                workers.join();
                 for (int k = 0; k < n; ++k)
                     if (!errors[size_t(k)].empty()) throw std::runtime_error("adaptive squares, device share " + std::to_string(k) + ": " + errors[size_t(k)]);
                 CUDA_CHECK(cudaSetDevice(device_));
@@ -2485,9 +2494,9 @@ void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partit
     // every device renders its share from its own host thread (a context's calls are blocking)
     std::vector<RenderStats> st(un);
     std::vector<std::string> errors(un);
-    std::vector<std::thread> threads;
+    ThreadGroup workers;
     for (int k = 0; k < n; ++k) {
-        threads.emplace_back([&, k]() {
+        workers.threads.emplace_back([&, k]() {
             try {
                 RenderParams q = p;
                 q.accumulate = 0;
@@ -2509,10 +2518,12 @@ void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partit
                 group[size_t(k)]->render_device(cam, q, accum[size_t(k)], count[size_t(k)], &st[size_t(k)], false);
             } catch (const std::exception& e) {
                 errors[size_t(k)] = e.what();
+            } catch (...) {
+                errors[size_t(k)] = "unknown error";
             }
         });
     }
-    for (auto& t : threads) t.join();
+    workers.join();
     for (int k = 0; k < n; ++k)
         if (!errors[size_t(k)].empty()) throw std::runtime_error("render_multi: device " + std::to_string(group[size_t(k)]->device()) + ": " + errors[size_t(k)]);
 
