@@ -386,8 +386,8 @@ __device__ __forceinline__ void merge_hit(const TraceIO& io, uint32_t ray_id, un
 #ifndef ARTB_EMIT_LANE_ATOMICS
 #define ARTB_EMIT_LANE_ATOMICS 1      // measured: -7 % on k_traverse against a warp scan + one atomic per warp
 #endif
-#ifndef ARTB_REFILL_MIN_IDLE
-#define ARTB_REFILL_MIN_IDLE 8        // a warp stops to fetch new rays once this many of its lanes are idle
+#ifndef ARTB_TRAVERSE_POP_LAST
+#define ARTB_TRAVERSE_POP_LAST 1      // 1: a lane learns that its walk has ended at the end of an iteration (refilled before the next node test)
 #endif
 extern __shared__ uint4 smem_nodes[];
 struct WarpFeed { float inv[3][32], c[3][32]; uint32_t octinv4[32], id[32]; };      // 1 KB per warp
@@ -516,13 +516,19 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
         }
         uint32_t prim_base = 0, prim_mask = 0;
         float tn_min = 0.f;
+#if !ARTB_TRAVERSE_POP_LAST
         if (active && !collect_pop(col, stack)) {
             if (spilled) mark_overflow(io.hits.at(id));
             active = false;
         }
         warp_sync();
-        if (active) collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, tn_min, s.one_bits, nullptr,
-                                 kSmemStack ? kSmemStack : ARTB_STACK_DEPTH);
+#endif
+        // (ARTB_TRAVERSE_POP_LAST: every active lane arrives here with a child to enter — the pop that finds the walk ended
+        // happens at the END of the previous iteration, so the lane is refilled before this node test instead of idling
+        // through it: one wasted node-test slot per ray less)
+        if (active && (!ARTB_TRAVERSE_POP_LAST || col.ng.y > 0x00ffffffu))
+            collect_node(nodes, br, t_min_f, t_max_f, col, stack, prim_base, prim_mask, tn_min, s.one_bits, nullptr,
+                         kSmemStack ? kSmemStack : ARTB_STACK_DEPTH);
         warp_sync();
         // append this step's pairs
         const uint32_t cnt = uint32_t(__popc(prim_mask));
@@ -558,6 +564,13 @@ k_traverse(TraceIO io, SceneView s, WaveCounters* c, int cur)
             }
         }
         warp_sync();
+#if ARTB_TRAVERSE_POP_LAST
+        if (active && !collect_pop(col, stack)) {     // nothing pending and the stack is empty: this ray is done
+            if (spilled) mark_overflow(io.hits.at(id));
+            active = false;
+        }
+        warp_sync();
+#endif
     }
     __syncthreads();
     if (threadIdx.x == 0) io.pb.region_count[blockIdx.x] = s_pairs < cap ? s_pairs : cap;

@@ -500,13 +500,9 @@ template <class NodePtr, class Stack>
 ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Traversal& tv, Stack& stack, const DRay& ray,
                             const BoxRay& br, double t_min, float t_min_f, TraversalStats* stats)
 {
-    if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
-        if (tv.sp == 0) tv.alive = false;
-        else {
-            tv.ng = stack[--tv.sp];
-            if (tv.ng.y <= 0x00ffffffu) { tv.pg = tv.ng; tv.ng = make_uint2(0u, 0u); }
-        }
-    }
+    // (A lane that has nothing pending pops its stack — or learns that its walk has ended — at the END of a round, below:
+    // a caller that refills lanes between rounds, k_walk, then hands such a lane its next ray BEFORE the following round
+    // instead of letting it idle through it. trav_begin leaves the root pending, so the first round needs no pop.)
     const uint32_t m_alive = warp_ballot(wm, tv.alive);
     if (m_alive == 0u) return 0u;
     const bool want_prims = tv.alive && tv.pg.y != 0u;
@@ -526,8 +522,8 @@ ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Trav
             warp_sync_mask(wm);
         }
         if (want_prims) tv.t_best_f = d2f_ru(tv.best.t);
-    } else if (tv.alive && !want_prims) {
-        // here ng holds at least one internal child: enter the one the ray meets first
+    } else if (tv.alive && !want_prims && tv.ng.y > 0x00ffffffu) {
+        // ng holds at least one internal child (always, except for a scene without a tree): enter the one the ray meets first
         const uint32_t hits = tv.ng.y;
         const int bit = find_msb(hits);
         tv.ng.y &= ~(1u << bit);
@@ -549,7 +545,14 @@ ARTB_HD uint32_t trav_round(const SceneView& s, NodePtr nodes, uint32_t wm, Trav
             prefetch_l1(pf + 64);
         }
     }
-    return m_alive;
+    if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
+        if (tv.sp == 0) tv.alive = false;
+        else {
+            tv.ng = stack[--tv.sp];
+            if (tv.ng.y <= 0x00ffffffu) { tv.pg = tv.ng; tv.ng = make_uint2(0u, 0u); }
+        }
+    }
+    return warp_ballot(wm, tv.alive);
 }
 
 // global surfaces: tested for every ray before the tree (same work for every lane, and an early t_max)
