@@ -1111,9 +1111,6 @@ k_extend(WaveBuffers w, SceneView s, RoundParams rp, int cur, int all)
 #ifndef ARTB_SHADE_BLOCKS
 #define ARTB_SHADE_BLOCKS 4
 #endif
-#ifndef ARTB_SHADE_LAZY_UV
-#define ARTB_SHADE_LAZY_UV 1          // 0: surface coordinates computed for every hit (the round-1 behaviour)
-#endif
 #ifndef ARTB_SHADE_BATCH
 #define ARTB_SHADE_BATCH 4            // iterations per queue reservation (1: the deferred per-iteration append)
 #endif
@@ -1224,15 +1221,8 @@ __global__ void __launch_bounds__(128, ARTB_SHADE_BLOCKS) k_shade(WaveBuffers w,
             if (next_valid && next_m != Q_REGEN) {
                 prefetch_l1(w.rays.at(next_slot)); prefetch_l1(w.aux.at(next_slot)); prefetch_l1(w.hits.at(next_slot));
             }
-            // surface coordinates only where the material's texture can look at them (image and barycentric textures; a
-            // checker may nest one): the sphere's acos / atan2 and the rectangle's two divisions are skipped otherwise
-            const FlatMaterial& mat = s.materials[s.prims[ph.prim].material];
-            bool need_uv = !ARTB_SHADE_LAZY_UV;
-            if (mat.type == MAT_LAMBERTIAN || mat.type == MAT_DIFFUSE_LIGHT || mat.type == MAT_ISOTROPIC) {
-                const uint32_t tt = s.textures[mat.texture].type;
-                need_uv = tt != TEX_SOLID && tt != TEX_NOISE;
-            }
-            const HitInfo h = need_uv ? make_hit_info<true>(s, ph.prim, r, ph.t) : make_hit_info<false>(s, ph.prim, r, ph.t);
+            const HitInfo h = make_hit_info(s, ph.prim, r, ph.t);
+            const FlatMaterial& mat = s.materials[h.material];
             key = 1;
             if (mat.type == MAT_DIFFUSE_LIGHT) {
                 const d3 e = material_emitted(s, mat, h);

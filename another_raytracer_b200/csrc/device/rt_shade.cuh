@@ -42,11 +42,7 @@ __device__ __forceinline__ void sphere_uv(d3 p, double& u, double& v)
     v = theta / ARTB_PI;
 }
 
-// Fill the record for primitive `prim` hit at parameter t by world-space ray `world`. kWithUv = false skips the surface
-// coordinates of spheres (acos + atan2) and rectangles (two divisions): k_shade passes it for hits whose material cannot
-// look at them (metal, dielectric, solid and Perlin textures — the latter read the hit POINT), which is most hits; every
-// other field is computed exactly as with them.
-template <bool kWithUv = true>
+// Fill the record for primitive `prim` hit at parameter t by world-space ray `world`.
 __device__ inline HitInfo make_hit_info(const SceneView& s, int32_t prim, const DRay& world, double t)
 {
     const FlatPrim& p = s.prims[prim];
@@ -70,7 +66,7 @@ __device__ inline HitInfo make_hit_info(const SceneView& s, int32_t prim, const 
         case PRIM_SPHERE: {
             const d3 outward = (h.p - ld3(p.g)) / p.g[3];          // sphere.h:59-62
             set_face_normal(h, r.d, outward);
-            if (kWithUv) sphere_uv(outward, h.u, h.v);
+            sphere_uv(outward, h.u, h.v);
             break;
         }
         case PRIM_MSPHERE: {
@@ -84,10 +80,8 @@ __device__ inline HitInfo make_hit_info(const SceneView& s, int32_t prim, const 
             if (p.type == PRIM_RECT_XY)      { a = r.o.x + t * r.d.x; b = r.o.y + t * r.d.y; outward = mk3(0, 0, 1); }
             else if (p.type == PRIM_RECT_XZ) { a = r.o.x + t * r.d.x; b = r.o.z + t * r.d.z; outward = mk3(0, 1, 0); }
             else                             { a = r.o.y + t * r.d.y; b = r.o.z + t * r.d.z; outward = mk3(1, 0, 0); }
-            if (kWithUv) {
-                h.u = (a - p.g[0]) / (p.g[1] - p.g[0]);
-                h.v = (b - p.g[2]) / (p.g[3] - p.g[2]);
-            }
+            h.u = (a - p.g[0]) / (p.g[1] - p.g[0]);
+            h.v = (b - p.g[2]) / (p.g[3] - p.g[2]);
             set_face_normal(h, r.d, outward);
             break;
         }
