@@ -590,11 +590,129 @@ struct WalkFeed { double ray[7][32]; float inv[3][32], c[3][32]; uint32_t octinv
 #ifndef ARTB_WALK_BLOCKS
 #define ARTB_WALK_BLOCKS 5             // 102 registers: measured +5.7 % over 4 blocks (128), 3 and 6 are slower
 #endif
+#ifndef ARTB_WALK_COOP
+#define ARTB_WALK_COOP 1               // the primitive step of k_walk is shared by the whole warp (walk_round)
+#endif
+#ifndef ARTB_WALK_COOP_MIN
+#define ARTB_WALK_COOP_MIN 24          // pending (ray, primitive) candidates in the warp that start a primitive step
+#endif
+#define ARTB_WALK_COOP_ITEMS 256
+
+// The warp's share of shared memory for the cooperative primitive step: the double-precision ray of every lane (node steps
+// only need the float BoxRay, so the lanes do not keep it in registers) and the list of pending (lane, primitive) candidates.
+struct WalkCoop { double ray[7][32]; uint32_t item[ARTB_WALK_COOP_ITEMS]; };                            // 2.75 KB per warp
+
+__device__ __forceinline__ DRay walk_coop_ray(const WalkCoop& co, uint32_t lane)
+{
+    DRay r;
+    r.o = mk3(co.ray[0][lane], co.ray[1][lane], co.ray[2][lane]);
+    r.d = mk3(co.ray[3][lane], co.ray[4][lane], co.ray[5][lane]);
+    r.tm = co.ray[6][lane];
+    return r;
+}
+
+// trav_round for k_walk (full warps, rays in shared memory). The node step is trav_round's. The PRIMITIVE step is taken by
+// the warp as a whole: in trav_round every lane tests its own candidates one after the other, so the double-precision
+// tests ran with the 9 lanes of 32 that happened to have a candidate left (profiles/r02_lines_k_walk.txt: more than half of
+// the kernel's samples). Here the pending candidates of all lanes are listed in shared memory and dealt out 32 at a time —
+// lane j tests candidate j against the ray of the lane that owns it, then the hits (few) are handed back to their owners
+// one by one through shuffles and merged with the same rule (hit_replaces, which does not depend on the order). A step
+// starts when ARTB_WALK_COOP_MIN candidates wait or no lane can take a node step.
+__device__ __forceinline__ void walk_round(const SceneView& s, Traversal& tv, uint2* stack, const BoxRay& br, WalkCoop& co,
+                                           double t_min, float t_min_f)
+{
+    const uint32_t full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m_alive = __ballot_sync(full, tv.alive);
+    if (m_alive == 0u) return;
+    const bool want_prims = tv.alive && tv.pg.y != 0u;
+    const uint32_t pend = want_prims ? tv.pg.y : 0u;
+    const uint32_t cnt = uint32_t(__popc(pend));
+    const uint32_t m_prims = __ballot_sync(full, want_prims);
+    const uint32_t total = __reduce_add_sync(full, cnt);
+    if (total >= uint32_t(ARTB_WALK_COOP_MIN) || (m_prims == m_alive && total != 0u)) {
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(full, incl, d);
+            if (int(lane) >= d) incl += v;
+        }
+        uint32_t k = incl - cnt;
+        uint32_t left = pend;
+        while (left != 0u && k < uint32_t(ARTB_WALK_COOP_ITEMS)) {
+            const int bit = find_msb(left);
+            left &= ~(1u << bit);
+            co.item[k++] = (lane << 27) | (tv.pg.x + uint32_t(bit));
+        }
+        if (want_prims) tv.pg.y = left;                   // candidates beyond the list wait for the next step
+        __syncwarp();
+        const uint32_t n_items = total < uint32_t(ARTB_WALK_COOP_ITEMS) ? total : uint32_t(ARTB_WALK_COOP_ITEMS);
+        for (uint32_t base = 0; base < n_items; base += 32u) {
+            const uint32_t j = base + lane;
+            const bool valid = j < n_items;
+            const uint32_t item = valid ? co.item[j] : (lane << 27);
+            const uint32_t owner = item >> 27;
+            ClosestHit cand;
+            cand.t = __shfl_sync(full, tv.best.t, int(owner));
+            cand.prim = -1; cand.dfs = 0;
+            if (valid) test_surface(s, item & 0x07ffffffu, walk_coop_ray(co, owner), t_min, cand);
+            uint32_t m_hit = __ballot_sync(full, valid && cand.prim >= 0);
+            while (m_hit != 0u) {
+                const int src = __ffs(int(m_hit)) - 1;
+                m_hit &= m_hit - 1u;
+                const uint32_t to = __shfl_sync(full, owner, src);
+                const double ht = __shfl_sync(full, cand.t, src);
+                const int32_t hp = __shfl_sync(full, cand.prim, src);
+                const uint32_t hd = __shfl_sync(full, cand.dfs, src);
+                if (lane == to) {
+                    bool take;
+                    if (ht < tv.best.t || tv.best.prim < 0) take = ht <= tv.best.t;
+                    else if (ht != tv.best.t) take = false;
+                    else take = tie_replaces(s.self, walk_coop_ray(co, lane), t_min, ht, uint32_t(hp), hd, uint32_t(tv.best.prim), tv.best.dfs);
+                    if (take) { tv.best.t = ht; tv.best.prim = hp; tv.best.dfs = hd; }
+                }
+            }
+        }
+        __syncwarp();
+        if (want_prims) tv.t_best_f = d2f_ru(tv.best.t);
+    } else if (tv.alive && !want_prims && tv.ng.y > 0x00ffffffu) {
+        const uint32_t hits = tv.ng.y;
+        const int bit = find_msb(hits);
+        tv.ng.y &= ~(1u << bit);
+        if (tv.ng.y > 0x00ffffffu && tv.sp < ARTB_STACK_DEPTH) stack[tv.sp++] = tv.ng;
+        const uint32_t slot = uint32_t(bit - 24) ^ (br.octinv4 & 0xffu);
+        const uint32_t rel = uint32_t(__popc(hits & ~(0xffffffffu << slot) & 0xffu));
+        const uint4* q = reinterpret_cast<const uint4*>(s.nodes + (tv.ng.x + rel));
+        const uint4 n0 = ld_node16(q), n1 = ld_node16(q + 1), n2 = ld_node16(q + 2), n3 = ld_node16(q + 3), n4 = ld_node16(q + 4);
+        float tn_unused = 0.f;
+        const uint32_t hitmask = node8_hits(n0, n1, n2, n3, n4, br, t_min_f, tv.t_best_f, s.one_bits, tn_unused);
+        tv.ng.x = n1.x;
+        tv.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+        tv.pg.x = n1.y;
+        tv.pg.y = hitmask & 0x00ffffffu;
+        if (tv.pg.y) {
+            const char* pf = reinterpret_cast<const char*>(s.prims + (tv.pg.x + uint32_t(find_msb(tv.pg.y))));
+            prefetch_l1(pf);
+            prefetch_l1(pf + 64);
+        }
+    }
+    if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
+        if (tv.sp == 0) tv.alive = false;
+        else {
+            tv.ng = stack[--tv.sp];
+            if (tv.ng.y <= 0x00ffffffu) { tv.pg = tv.ng; tv.ng = make_uint2(0u, 0u); }
+        }
+    }
+}
 template <bool kBatch>
 __global__ void __launch_bounds__(ARTB_WALK_THREADS, ARTB_WALK_BLOCKS)
 k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
 {
     __shared__ WalkFeed feeds[ARTB_WALK_THREADS / 32];
+#if ARTB_WALK_COOP
+    __shared__ WalkCoop coops[ARTB_WALK_THREADS / 32];
+    WalkCoop& coop = coops[threadIdx.x >> 5];
+#endif
     const uint32_t n = *io.n_ptr;
     if (!kBatch && blockIdx.x == 0 && threadIdx.x == 0) {
         // the free list k_shade(cur^1) just consumed: account the samples it started, then clear it
@@ -616,9 +734,14 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
     Traversal tv;
     trav_begin(tv, io.t_max, false);
     tv.alive = false;
+#if ARTB_WALK_COOP
+    BoxRay br;
+    br.inv[0] = br.inv[1] = br.inv[2] = 1.f; br.c[0] = br.c[1] = br.c[2] = 0.f; br.octinv4 = 0x07070707u;
+#else
     DRay ray;
     ray.o = mk3(0, 0, 0); ray.d = mk3(1, 0, 0); ray.tm = 0;
     BoxRay br = make_box_ray(ray);
+#endif
     uint32_t id = 0;
     bool has = false;                 // this lane holds a ray whose result is not stored yet
     for (;;) {
@@ -656,9 +779,14 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
                 const uint32_t rank = uint32_t(__popc(idle & lt_mask));
                 if (!tv.alive && rank < take) {
                     const uint32_t e = feed_count - 1u - rank;
+#if ARTB_WALK_COOP
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) coop.ray[k][lane] = feed.ray[k][e];
+#else
                     ray.o = mk3(feed.ray[0][e], feed.ray[1][e], feed.ray[2][e]);
                     ray.d = mk3(feed.ray[3][e], feed.ray[4][e], feed.ray[5][e]);
                     ray.tm = feed.ray[6][e];
+#endif
                     br.inv[0] = feed.inv[0][e]; br.inv[1] = feed.inv[1][e]; br.inv[2] = feed.inv[2][e];
                     br.c[0] = feed.c[0][e]; br.c[1] = feed.c[1][e]; br.c[2] = feed.c[2][e];
                     br.octinv4 = feed.octinv4[e];
@@ -675,7 +803,11 @@ k_walk(TraceIO io, SceneView s, WaveCounters* c, int cur)
                 continue;
             }
         }
+#if ARTB_WALK_COOP
+        walk_round(s, tv, stack, br, coop, io.t_min, t_min_f);
+#else
         trav_round(s, s.nodes, 0xffffffffu, tv, stack, ray, br, io.t_min, t_min_f, nullptr);
+#endif
     }
 }
 
