@@ -597,12 +597,6 @@ struct WalkFeed { double ray[7][32]; float inv[3][32], c[3][32]; uint32_t octinv
 #define ARTB_WALK_COOP_MIN 24          // pending (ray, primitive) candidates in the warp that start a primitive step
 #endif
 #define ARTB_WALK_COOP_ITEMS 256
-#ifndef ARTB_WALK_PREFETCH_ALL
-#define ARTB_WALK_PREFETCH_ALL 0
-#endif
-#ifndef ARTB_WALK_PREFETCH_NODE
-#define ARTB_WALK_PREFETCH_NODE 0
-#endif
 
 // The warp's share of shared memory for the cooperative primitive step: the double-precision ray of every lane (node steps
 // only need the float BoxRay, so the lanes do not keep it in registers) and the list of pending (lane, primitive) candidates.
@@ -696,29 +690,11 @@ __device__ __forceinline__ void walk_round(const SceneView& s, Traversal& tv, ui
         tv.ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
         tv.pg.x = n1.y;
         tv.pg.y = hitmask & 0x00ffffffu;
-#if ARTB_WALK_PREFETCH_NODE
-        if (tv.ng.y > 0x00ffffffu) {          // the child the next node step enters
-            const uint32_t nslot = uint32_t(find_msb(tv.ng.y) - 24) ^ (br.octinv4 & 0xffu);
-            const char* nf = reinterpret_cast<const char*>(s.nodes + (tv.ng.x + uint32_t(__popc(tv.ng.y & ~(0xffffffffu << nslot) & 0xffu))));
-            prefetch_l1(nf);
-            prefetch_l1(nf + 64);
-        }
-#endif
-#if ARTB_WALK_PREFETCH_ALL
-        for (uint32_t m = tv.pg.y; m != 0u; ) {
-            const int b = find_msb(m);
-            m &= ~(1u << b);
-            const char* pf = reinterpret_cast<const char*>(s.prims + (tv.pg.x + uint32_t(b)));
-            prefetch_l1(pf);
-            prefetch_l1(pf + 64);
-        }
-#else
         if (tv.pg.y) {
             const char* pf = reinterpret_cast<const char*>(s.prims + (tv.pg.x + uint32_t(find_msb(tv.pg.y))));
             prefetch_l1(pf);
             prefetch_l1(pf + 64);
         }
-#endif
     }
     if (tv.alive && tv.pg.y == 0u && tv.ng.y <= 0x00ffffffu) {
         if (tv.sp == 0) tv.alive = false;
