@@ -596,7 +596,9 @@ struct WalkFeed { double ray[7][32]; float inv[3][32], c[3][32]; uint32_t octinv
 #ifndef ARTB_WALK_COOP_MIN
 #define ARTB_WALK_COOP_MIN 24          // pending (ray, primitive) candidates in the warp that start a primitive step
 #endif
+#ifndef ARTB_WALK_COOP_ITEMS
 #define ARTB_WALK_COOP_ITEMS 256
+#endif
 
 // The warp's share of shared memory for the cooperative primitive step: the double-precision ray of every lane (node steps
 // only need the float BoxRay, so the lanes do not keep it in registers) and the list of pending (lane, primitive) candidates.
