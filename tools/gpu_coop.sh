@@ -1,4 +1,3 @@
 #!/bin/bash
-# k_walk with a 32-entry candidate list and a step started by any candidate: the list-overflow path of walk_round under the parity suites
-ARTB_LIB=$PWD/another_raytracer_b200/libartb_items32.so timeout 900 python -m pytest tests/test_gpu_walk_parity.py tests/test_gpu_bvh_build.py -x -q -m gpu 2>&1 | tail -3
-ARTB_LIB=$PWD/another_raytracer_b200/libartb_items32.so ARTB_TWO_PHASE=0 timeout 900 python -m pytest tests/test_gpu_trace_parity.py -x -q -m gpu 2>&1 | tail -3
+# k_walk variants: slot-swapped refill, lane-count rule, against the previous build
+echo "== heightfield"; C5=1 timeout 1200 bash tools/bench_variants.sh --workload heightfield --spp-per-step 32
