@@ -58,7 +58,7 @@ def ncu_traffic(workload: str):
     p = ROOT / "profiles" / "traffic.json"
     try:
         t = json.loads(p.read_text())[workload]
-        return {"bytes_per_launch": int(sum(v for k, v in t["kernels"].items() if k in ("k_traverse", "k_pairs", "k_finish", "k_walk"))),
+        return {"bytes_per_launch": int(sum(v for k, v in t["kernels"].items() if k in ("k_traverse", "k_pairs", "k_finish", "k_walk", "k_bin"))),
                 "per_kernel": t["kernels"], "source": t.get("source")}
     except Exception:
         return None

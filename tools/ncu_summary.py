@@ -61,8 +61,9 @@ def report(path):
             print(f"{key:90s} [{rows[1][i]}] {[r[i] for r in rows[2:]]}")
 
 
-def traffic(path):
-    """profiles/traffic.json: mean dram__bytes_read.sum + dram__bytes_write.sum per launch of every captured kernel"""
+def traffic(path, workload=None, note=None):
+    """mean dram__bytes_read.sum + dram__bytes_write.sum per launch of every captured kernel; with a workload name the
+    entry of that workload in profiles/traffic.json is replaced (bench.py reads it as roofline.traffic)"""
     import json
     import re
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -76,8 +77,16 @@ def traffic(path):
         agg[name].append(float(r[rd].replace(",", "")) * scale[units[rd]] + float(r[wr].replace(",", "")) * scale[units[wr]])
     res = {"source": f"{path}: ncu --set full --clock-control none, mean over the captured launches (steady-state waves of bench.py)",
            "kernels": {k: int(sum(v) / len(v)) for k, v in agg.items()}}
+    if note:
+        res["source"] = res["source"].replace(": ncu", f" ({note}): ncu", 1)
     print(json.dumps(res, indent=1))
+    if workload:
+        import pathlib
+        f = pathlib.Path(__file__).resolve().parent.parent / "profiles" / "traffic.json"
+        t = json.loads(f.read_text()) if f.exists() else {}
+        t[workload] = res
+        f.write_text(json.dumps(t, indent=1) + "\n")
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
