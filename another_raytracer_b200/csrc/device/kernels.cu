@@ -967,6 +967,9 @@ __device__ __forceinline__ void flush_batched_appends(int (*keys)[kThreads], uin
     }
 }
 
+#ifndef ARTB_FINISH_SCREEN
+#define ARTB_FINISH_SCREEN 1          // global rectangles are screened in float before the exact tests (rect_certain_miss)
+#endif
 #ifndef ARTB_FINISH_BATCH
 #define ARTB_FINISH_BATCH 1           // iterations per queue reservation in k_finish (1: reserve every iteration; 4 and 8 measured the same)
 #endif
@@ -999,6 +1002,20 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     WaveCounters* c = w.c;
     const uint32_t n_surf = s.n_global_prims - s.n_global_media;
     const uint32_t stride = gridDim.x * blockDim.x;
+#if ARTB_FINISH_SCREEN
+    // float screens of the first 32 global surfaces (rect_certain_miss), built once per block
+    __shared__ RectScreen s_screen[kSurf ? 32 : 1];
+    __shared__ uint32_t s_screen_mask;
+    if (kSurf) {
+        if (threadIdx.x == 0) s_screen_mask = 0u;
+        __syncthreads();
+        if (threadIdx.x < 32u && threadIdx.x < n_surf) {
+            RectScreen q;
+            if (rect_screen_make(s.prims[threadIdx.x], q)) { s_screen[threadIdx.x] = q; atomicOr(&s_screen_mask, 1u << threadIdx.x); }
+        }
+        __syncthreads();
+    }
+#endif
     // The ray id of the NEXT iteration is loaded one iteration ahead and its records are prefetched while this
     // iteration computes; all records of this iteration are requested together, before anything waits on them.
     uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
@@ -1052,7 +1069,30 @@ k_finish(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
             ClosestHit best;
             best.t = ph.t; best.prim = ph.prim; best.dfs = ph.dfs & ~ARTB_HIT_TIED;
             if (tied) best = replay_ties(s.self, io.ties.at(id), n_tied, uint32_t(ph.prim), r, io.t_min, io.t_max);
+#if ARTB_FINISH_SCREEN
+            if (kSurf) {
+                // every lane screens all rectangles in float, then takes only its own candidates through the exact tests
+                const uint32_t n_first = n_surf < 32u ? n_surf : 32u;
+                uint32_t cand = n_first == 32u ? 0xffffffffu : (1u << n_first) - 1u;
+                if (s_screen_mask) {
+                    const float of[3] = { float(r.o.x), float(r.o.y), float(r.o.z) }, df[3] = { float(r.d.x), float(r.d.y), float(r.d.z) };
+                    const float inv[3] = { 1.0f / df[0], 1.0f / df[1], 1.0f / df[2] };
+                    const float t_lo = d2f_rd(io.t_min), t_hi = d2f_ru(best.t);
+                    for (uint32_t m = s_screen_mask; m != 0u; m &= m - 1u) {
+                        const int i = __ffs(int(m)) - 1;
+                        if (rect_certain_miss(s_screen[i], of, df, inv, t_lo, t_hi)) cand &= ~(1u << i);
+                    }
+                }
+                while (cand != 0u) {
+                    const int i = __ffs(int(cand)) - 1;
+                    cand &= cand - 1u;
+                    test_surface(s, uint32_t(i), r, io.t_min, best);
+                }
+                for (uint32_t i = 32u; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
+            }
+#else
             if (kSurf) for (uint32_t i = 0; i < n_surf; ++i) test_surface(s, i, r, io.t_min, best);
+#endif
             if (kMedia && s.n_global_media) {
                 MediumXi xi;
                 if (kBatch) {

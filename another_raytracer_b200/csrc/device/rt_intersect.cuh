@@ -101,6 +101,47 @@ ARTB_HD bool rect_t(uint32_t type, const double* g, const DRay& r, double t_min,
     return true;
 }
 
+// FP32 screen for rect_t: true only when the double-precision test above CERTAINLY returns false, so skipping the test
+// cannot change a result. k_finish runs it over the global rectangles of a scene (the five walls and the light of a
+// Cornell box) for all lanes at once and then hands each lane only its own surviving candidates: the exact tests ran
+// one rectangle after the other with the 5 lanes of 32 that happened to hit it (profiles/r02_cornell_kernels.txt).
+// Every float quantity carries an error bound that covers the roundings of the inputs (2^-24 each), of 1/d (2^-23) and of
+// the operations, with a factor 2-4 to spare; a NaN or an infinity anywhere makes every comparison false, i.e. "not
+// certain", and the exact test decides.
+struct RectScreen { float k, a0, a1, b0, b1; uint32_t axes; };     // axes: k | a << 2 | b << 4; a0, b0 rounded down, a1, b1 up
+
+ARTB_HD bool rect_screen_make(const FlatPrim& p, RectScreen& q)      // false: not an untransformed rectangle
+{
+    if (p.xform != 0u || (p.type != PRIM_RECT_XY && p.type != PRIM_RECT_XZ && p.type != PRIM_RECT_YZ)) return false;
+    q.axes = p.type == PRIM_RECT_XY ? (2u | 0u << 2 | 1u << 4) : p.type == PRIM_RECT_XZ ? (1u | 0u << 2 | 2u << 4) : (0u | 1u << 2 | 2u << 4);
+    q.a0 = d2f_rd(p.g[0]); q.a1 = d2f_ru(p.g[1]); q.b0 = d2f_rd(p.g[2]); q.b1 = d2f_ru(p.g[3]);
+    q.k = float(p.g[4]);
+    return true;
+}
+
+// o, d: the ray rounded to float; inv = fl(1 / d); t_min_f <= t_min and t_max_f >= t_max of the exact test
+ARTB_HD bool rect_certain_miss_axes(const RectScreen& q, float ok, float ik, float oa, float da, float ob, float db, float t_min_f, float t_max_f)
+{
+    const float e21 = 4.76837158203125e-07f;        // 2^-21
+    const float tt = (q.k - ok) * ik;
+    const float et = fabsf(ik) * (fabsf(q.k) + fabsf(ok)) * e21 + fabsf(tt) * e21 + 1e-30f;
+    if (tt + et < t_min_f || tt - et > t_max_f) return true;
+    const float pa = tt * da, pb = tt * db;
+    const float a = pa + oa, b = pb + ob;
+    const float ea = et * fabsf(da) * 1.01f + (fabsf(oa) + fabsf(pa)) * e21 + 1e-30f;
+    const float eb = et * fabsf(db) * 1.01f + (fabsf(ob) + fabsf(pb)) * e21 + 1e-30f;
+    return a + ea < q.a0 || a - ea > q.a1 || b + eb < q.b0 || b - eb > q.b1;
+}
+
+ARTB_HD bool rect_certain_miss(const RectScreen& q, const float o[3], const float d[3], const float inv[3], float t_min_f, float t_max_f)
+{
+    // (the plane's axis is the same for every lane of a warp: a uniform branch, and no dynamically indexed arrays)
+    const uint32_t ak = q.axes & 3u;
+    if (ak == 2u) return rect_certain_miss_axes(q, o[2], inv[2], o[0], d[0], o[1], d[1], t_min_f, t_max_f);
+    if (ak == 1u) return rect_certain_miss_axes(q, o[1], inv[1], o[0], d[0], o[2], d[2], t_min_f, t_max_f);
+    return rect_certain_miss_axes(q, o[0], inv[0], o[1], d[1], o[2], d[2], t_min_f, t_max_f);
+}
+
 ARTB_HD bool triangle_t(const double* g, const DRay& r, double t_min, double t_max, double& t)
 {
     // triangle.h:28-76

@@ -68,4 +68,29 @@ int hostsim_trace(const artb_flat_scene* f, const double* rays, uint64_t n, doub
     return 0;
 }
 
+// The float screen k_finish puts in front of the exact rectangle test (rect_certain_miss), next to the exact test itself:
+// out[i] bit 0 = rect_t() hits within (t_min, t_max[i]], bit 1 = the screen calls ray i a certain miss. The two bits must
+// never be set together. type: ARTB_PRIM_RECT_XY / XZ / YZ; g = a0 a1 b0 b1 k; t_max: one value per ray.
+int hostsim_rect_screen(int type, const double* g, const double* rays, uint64_t n, double t_min, const double* t_max, uint8_t* out)
+{
+    FlatPrim p{};
+    p.type = uint32_t(type);
+    for (int k = 0; k < 5; ++k) p.g[k] = g[k];
+    RectScreen q;
+    if (!rect_screen_make(p, q)) return 1;
+    for (uint64_t i = 0; i < n; ++i) {
+        DRay r;
+        r.o = mk3(rays[i * 7 + 0], rays[i * 7 + 1], rays[i * 7 + 2]);
+        r.d = mk3(rays[i * 7 + 3], rays[i * 7 + 4], rays[i * 7 + 5]);
+        r.tm = rays[i * 7 + 6];
+        double t = 0;
+        const bool hit = rect_t(p.type, p.g, r, t_min, t_max[i], t);
+        const float of[3] = { float(r.o.x), float(r.o.y), float(r.o.z) }, df[3] = { float(r.d.x), float(r.d.y), float(r.d.z) };
+        const float inv[3] = { 1.0f / df[0], 1.0f / df[1], 1.0f / df[2] };
+        const bool miss = rect_certain_miss(q, of, df, inv, d2f_rd(t_min), d2f_ru(t_max[i]));
+        out[i] = uint8_t((hit ? 1 : 0) | (miss ? 2 : 0));
+    }
+    return 0;
+}
+
 }

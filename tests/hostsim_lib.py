@@ -50,3 +50,16 @@ def trace(scene, rays, t_min=0.001, t_max=float("inf"), xi=None, per_ray=False, 
     if per_ray:
         st["per_ray"] = pr
     return out, st
+
+
+def rect_screen(prim_type, g, rays, t_min, t_max):
+    """bit 0: the exact rectangle test hits, bit 1: the float screen of k_finish calls the ray a certain miss"""
+    lib = load()
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 7)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    t_max = np.ascontiguousarray(np.broadcast_to(np.asarray(t_max, dtype=np.float64), (len(rays),)))
+    out = np.zeros(len(rays), dtype=np.uint8)
+    lib.hostsim_rect_screen.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_void_p, C.c_void_p]
+    rc = lib.hostsim_rect_screen(int(prim_type), g.ctypes.data, rays.ctypes.data, len(rays), float(t_min), t_max.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    return out
