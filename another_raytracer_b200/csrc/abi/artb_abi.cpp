@@ -540,7 +540,7 @@ int artb_render_device(artb_ctx* ctx, const artb_camera* cam, const artb_render_
     if (p->mode == ARTB_MODE_VARIANCE_MASK && !count_dev) return fail(ctx, ARTB_E_INVALID, "variance-mask mode needs a count buffer");
     return guarded(ctx, [&]() -> int {
         RenderStats s;
-        ctx->renderer->render_device(make_camera(*cam), to_params(*p), accum_dev, count_dev, &s, p->profile != 0);
+        ctx->renderer->render_device(make_camera(*cam), to_params(*p), accum_dev, count_dev, &s, p->profile > 0 ? p->profile : 0);
         to_stats(s, stats);
         return ARTB_OK;
     });

@@ -2164,7 +2164,7 @@ void Renderer::build_bvh_device(int max_leaf_prims, BvhBuildStats* stats)
 }
 
 void Renderer::render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
-                             RenderStats* stats, bool profile)
+                             RenderStats* stats, int profile_every)
 {
     if (!has_scene_) throw std::runtime_error("render: no scene uploaded");
     if (p.width < 2 || p.height < 2 || p.samples_per_pixel < 1 || p.max_depth < 1)
@@ -2260,7 +2260,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
     // per-wave events around the kernels of the closest-hit stage (roofline denominator), drained whenever the pool
     // fills up: [5k] before k_traverse, [5k+1] after it, [5k+2] after k_pairs, [5k+3] after k_finish, [5k+4] after k_extend
     const size_t kPairs = 1024;
-    if (profile && I.ev.size() < kPairs * 5) {
+    if (profile_every > 0 && I.ev.size() < kPairs * 5) {
         I.ev.resize(kPairs * 5);
         for (auto& e : I.ev) CUDA_CHECK(cudaEventCreate(&e));
     }
@@ -2307,6 +2307,9 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
             for (int k = 0; k < n_waves; ++k) {
                 k_shade<<<shade_blocks, 128, 0, st>>>(w, view_, rp, cur);
                 cur ^= 1;
+                // profile = N: every N-th wave carries the events (five records per wave cost 1.7 % of a render when every
+                // wave has them; the per-kernel averages of a systematic sample are the same)
+                const bool profile = profile_every > 0 && S.waves % (unsigned long long)profile_every == 0;
                 if (profile) {
                     if (pairs_used == kPairs) drain();
                     CUDA_CHECK(cudaEventRecord(I.ev[5 * pairs_used], st));
@@ -2401,7 +2404,7 @@ void Renderer::render_device(const CameraParams& cam, const RenderParams& p, flo
 
     CUDA_CHECK(cudaEventRecord(ev_end, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (profile) drain();
+    if (profile_every > 0) drain();
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev_begin, ev_end));
     S.elapsed_ms = ms;
@@ -2536,7 +2539,7 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
                             qq.n_pixel_list = e - b;
                             if (k == 0) {
                                 qq.pixel_list_dev = L.pixels + b;
-                                if (e > b) render_device(cam, qq, accum_dev, nullptr, &rs[0], false);
+                                if (e > b) render_device(cam, qq, accum_dev, nullptr, &rs[0], 0);
                                 return;
                             }
                             Renderer* pr = peers[k - 1];
@@ -2547,7 +2550,7 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
                             if (e > b) CUDA_CHECK(cudaMemcpyPeer(list_k, pr->device(), L.pixels + b, device_, size_t(e - b) * sizeof(uint32_t)));
                             qq.pixel_list_dev = list_k;
                             qq.accumulate = 0;
-                            if (e > b) pr->render_device(cam, qq, pacc[size_t(k - 1)], nullptr, &rs[size_t(k)], false);
+                            if (e > b) pr->render_device(cam, qq, pacc[size_t(k - 1)], nullptr, &rs[size_t(k)], 0);
                             else CUDA_CHECK(cudaMemset(pacc[size_t(k - 1)], 0, n_pixels * 3 * sizeof(float)));
                         } catch (const std::exception& ex) {
                             errors[size_t(k)] = ex.what();
@@ -2577,7 +2580,7 @@ void Renderer::render_adaptive_squares(const CameraParams& cam, const RenderPara
             } else if (n_px) {
                 q.pixel_list_dev = L.pixels; q.n_pixel_list = n_px;
                 RenderStats r;
-                render_device(cam, q, accum_dev, nullptr, &r, false);
+                render_device(cam, q, accum_dev, nullptr, &r, 0);
                 S.samples += r.samples; S.rays += r.rays; S.waves += r.waves; S.launches += r.launches;
                 k_sq_commit<<<(n_px + 255) / 256, 256, 0, st>>>(L.pixels, n_px, accum_dev, p.samples_per_pixel, work, count_dev);
             }
@@ -2641,7 +2644,7 @@ void Renderer::render_host(const CameraParams& cam, const RenderParams& p, uint8
     if (p.adaptive == 2) {
         render_adaptive_squares(cam, q, rgb, accum, count, stats);
     } else {
-        render_device(cam, q, accum, count, stats, false);
+        render_device(cam, q, accum, count, stats, 0);
         resolve_device(accum, count, int(n_pixels), p.adaptive ? 0 : p.samples_per_pixel, rgb);
     }
     if (rgb_out) CUDA_CHECK(cudaMemcpy(rgb_out, rgb, n_pixels * 3, cudaMemcpyDeviceToHost));
@@ -2706,7 +2709,7 @@ void Renderer::render_host_multi(Renderer* const* peers, int n_peers, int partit
                     CUDA_CHECK(cudaMemset(count[size_t(k)], 0, n_pixels * sizeof(uint32_t)));
                     return;
                 }
-                group[size_t(k)]->render_device(cam, q, accum[size_t(k)], count[size_t(k)], &st[size_t(k)], false);
+                group[size_t(k)]->render_device(cam, q, accum[size_t(k)], count[size_t(k)], &st[size_t(k)], 0);
             } catch (const std::exception& e) {
                 errors[size_t(k)] = e.what();
             } catch (...) {

@@ -38,7 +38,7 @@ struct RenderStats {
     unsigned long long rays = 0;      // closest-hit queries (engine.h:455)
     unsigned long long waves = 0;
     unsigned long long launches = 0;  // kernels launched
-    double extend_ms = 0;             // profile=1: the closest-hit stage (k_traverse + k_pairs + k_finish + k_extend), per-wave events
+    double extend_ms = 0;             // profile=N: every N-th wave timed; the closest-hit stage (k_traverse + k_pairs + k_finish + k_extend), per-wave events
     double traverse_ms = 0, pairs_ms = 0, finish_ms = 0;
     unsigned long long overflow_rays = 0;   // rays whose candidate list overflowed (traced by the one-phase pass)
     unsigned long long extend_launches = 0;
@@ -87,7 +87,7 @@ public:
 
     // Wavefront render into a device accumulation buffer (W*H*3 float sums) + per-pixel sample counts.
     void render_device(const CameraParams& cam, const RenderParams& p, float* accum_dev, uint32_t* count_dev,
-                       RenderStats* stats, bool profile);
+                       RenderStats* stats, int profile_every);
     // engine_mode::adaptive of the reference (engine.h:151-333): corners of 12/6/3-pixel squares traced at full spp,
     // the rest interpolated. Device buffers: rgb W*H*3, accum W*H*3 sums of the traced pixels, count = spp where traced.
     // peers (optional): the pixels each level asks for are split evenly over this device and the peers; their frames are

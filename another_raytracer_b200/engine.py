@@ -200,7 +200,7 @@ class RenderOptions:
     adaptive_batch_spp: int = 8
     adaptive_threshold: float = 0.02
     accumulate: bool = False
-    profile: bool = False
+    profile: int = 0              # N > 0: the kernels of every N-th wave are timed with CUDA events (stats extend_ms, traverse_ms ...)
 
     def to_c(self) -> _abi.RenderParams:
         return _abi.RenderParams(self.width, self.height, self.samples_per_pixel, self.max_depth, self.seed, self.stream,

@@ -39,6 +39,8 @@ os.environ.setdefault("ARTB_ASSETS", str(ROOT / "assets"))
 
 # algorithmic bytes per ray on the REFERENCE's trees: 32 B per node visit + primitive records + 128 B state
 B_RAY = {1: 2354, 6: 768, 7: 768, 8: 1322, 9: 1275, 10: 1346, 11: 539}
+PROFILE_EVERY = 8          # the kernels of every 8th wave are timed with CUDA events (roofline.avg_launch_ms and the per-kernel times)
+
 WORKLOADS = {
     "final": dict(alias=8, width=800, height=800, name="next_week_final_scene_800x800", full_spp=10000),
     "cornell": dict(alias=6, width=600, height=600, name="cornell_box_600x600", full_spp=1000),
@@ -279,7 +281,7 @@ def run_cuda_arm(args, wl):
             # partition A (default): every rank renders S samples of every pixel on its own Philox stream and index range;
             # partition B (--partition tiles, BASELINE configs[4]): every rank renders S samples of its interleaved tiles
             opt = A.RenderOptions(W, H, S, seed=args.seed, stream=0 if tiles else rank,
-                                  sample_begin=(k if tiles else k * world + rank) * S, profile=True,
+                                  sample_begin=(k if tiles else k * world + rank) * S, profile=PROFILE_EVERY,
                                   tile_parts=world if tiles else 1, tile_part=rank if tiles else 0,
                                   mode=1 if args.variance_mask else 0)
             st = ctx.render_device(cam, opt, step_accum.data_ptr(), step_count.data_ptr() if step_count is not None else None)
@@ -382,17 +384,21 @@ def run_cuda_arm(args, wl):
         peak, peak_src = measured_peak_gbs()
         b_ray = B_RAY.get(alias)
         roofline = None
+        waves = sum(s["waves"] for s in stats)
         if b_ray and ext_ms > 0:
-            achieved = b_ray * rank0_rays / (ext_ms * 1e-3) / 1e9
+            # the kernels of every PROFILE_EVERY-th wave are timed (events on every wave cost 1.7 % of the step): mean rays per
+            # wave over ALL waves / mean time of the timed waves
+            achieved = b_ray * (rank0_rays / max(waves, 1)) / (ext_ms / max(ext_launches, 1) * 1e-3) / 1e9
             tr = ncu_traffic(args.workload)
             roofline = {"bound": "hbm", "kernel": "closest-hit stage = k_traverse + k_pairs + k_finish (+ k_extend overflow pass)",
                         "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": tr["bytes_per_launch"] if tr else None,
                         "traffic_per_kernel": tr["per_kernel"] if tr else None, "traffic_source": tr["source"] if tr else None,
                         "peak_source": peak_src,
-                        "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rank0_rays / max(ext_launches, 1),
-                        "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(ext_launches),
-                        "extend_share_of_step": ext_ms / max(sum(s["elapsed_ms"] for s in stats), 1e-9),
+                        "algorithmic_bytes_per_ray": b_ray, "rays_per_launch": rank0_rays / max(waves, 1),
+                        "avg_launch_ms": ext_ms / max(ext_launches, 1), "launches": int(waves), "launches_timed": int(ext_launches),
+                        "timed_every": PROFILE_EVERY,
+                        "extend_share_of_step": (ext_ms / max(ext_launches, 1)) * waves / max(sum(s["elapsed_ms"] for s in stats), 1e-9),
                         "traverse_ms_per_launch": sum(s["traverse_ms"] for s in stats) / max(ext_launches, 1),
                         "pairs_ms_per_launch": sum(s["pairs_ms"] for s in stats) / max(ext_launches, 1),
                         "finish_ms_per_launch": sum(s["finish_ms"] for s in stats) / max(ext_launches, 1),

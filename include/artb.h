@@ -218,7 +218,7 @@ typedef struct artb_render_params {
     int32_t adaptive_min_spp, adaptive_batch_spp;
     double adaptive_threshold;          /* relative standard error of the pixel luminance mean */
     int32_t accumulate;                 /* device variant: add to the buffers instead of clearing them */
-    int32_t profile;                    /* time every extend launch with CUDA events (stats.extend_ms) */
+    int32_t profile;                    /* N > 0: time the kernels of every N-th wave with CUDA events (stats.extend_ms, extend_launches = waves timed) */
 } artb_render_params;
 
 typedef struct artb_stats {
@@ -227,7 +227,7 @@ typedef struct artb_stats {
     double extend_ms; uint64_t extend_launches;
     uint64_t pixels_active, pixels_converged;
     uint64_t h2d_bytes, d2h_bytes;
-    double traverse_ms, pairs_ms, finish_ms;   /* profile=1: the kernels of the closest-hit stage (extend_ms = whole stage) */
+    double traverse_ms, pairs_ms, finish_ms;   /* profile=N: the kernels of the closest-hit stage in the timed waves (extend_ms = whole stage) */
     uint64_t overflow_rays;             /* rays traced by the one-phase overflow pass */
     /* contexts with several devices: elapsed_ms = slowest device + the exchange; counts are summed over the devices */
     int32_t n_devices, reserved;
