@@ -39,7 +39,9 @@ namespace artb {
 // needs the ray, the path's bookkeeping and its hit record touches exactly one aligned line (four sectors) per path.
 // (As three separate arrays the 16- and 32-byte records dragged their neighbours' sectors along on every random
 // access: ncu showed 320 B of DRAM reads per ray in k_finish for 116 B of payload.)
-#define ARTB_PATH_STRIDE 128
+#ifndef ARTB_PATH_STRIDE
+#define ARTB_PATH_STRIDE 128          // (256 / 512: probes of the address-translation reach — same lines touched, 2-4x the pages)
+#endif
 template <class T>
 struct Strided {
     char* base; uint32_t stride;
