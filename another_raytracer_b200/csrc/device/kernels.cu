@@ -973,7 +973,13 @@ __device__ __forceinline__ void flush_batched_appends(int (*keys)[kThreads], uin
 #define ARTB_FINISH_SCREEN 1          // global rectangles are screened in float before the exact tests (rect_certain_miss)
 #endif
 #ifndef ARTB_FINISH_BATCH
-#define ARTB_FINISH_BATCH 1           // iterations per queue reservation in k_finish (1: reserve every iteration; 4 and 8 measured the same)
+#define ARTB_FINISH_BATCH 16          // iterations per queue reservation in k_finish. On the final scene and the Cornell box 1, 4, 8 and
+                                      // 16 measure the same (500.6 / 493.5 / 499.6 / 500.8 Msamples/s); on the mesh scenes, where half of a
+                                      // wave's rays end in the sky (free-slot queue) and the other half on ONE material, every warp hits
+                                      // the same two counters every iteration and the wait for the append position was the top stall of
+                                      // the kernel (15 % of its samples, profiles/r02_lines_k_finish_cow.txt): k_finish 0.254 -> 0.167 ms
+                                      // (8) -> 0.145 ms (16) on the cow, 0.242 -> 0.147 -> 0.134 ms on the dino (+17.6 % / +26.7 %
+                                      // samples/s in all)
 #endif
 #ifndef ARTB_FINISH_DEFER
 #define ARTB_FINISH_DEFER 0           // deferred queue appends cost k_finish more in spills than the hidden latency gains
@@ -1178,6 +1184,9 @@ __device__ __noinline__ void bin_resolve_tie(const SceneView* scene, PathHit* hi
 #ifndef ARTB_BIN_BLOCKS
 #define ARTB_BIN_BLOCKS 8
 #endif
+#ifndef ARTB_BIN_BATCH
+#define ARTB_BIN_BATCH 8              // iterations per queue reservation (as ARTB_FINISH_BATCH): height field +7.5 %; 16 spills at the 32 registers of k_bin
+#endif
 __global__ void __launch_bounds__(ARTB_BIN_THREADS, ARTB_BIN_BLOCKS)
 k_bin(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
 {
@@ -1185,6 +1194,12 @@ k_bin(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
     const int lane = threadIdx.x & 31;
     WaveCounters* c = w.c;
     const uint32_t stride = gridDim.x * blockDim.x;
+#if ARTB_BIN_BATCH > 1
+    __shared__ int s_keys[ARTB_BIN_BATCH][ARTB_BIN_THREADS];
+    __shared__ uint32_t s_ids[ARTB_BIN_BATCH][ARTB_BIN_THREADS];
+    int n_parked = 0;                  // warp-uniform: iterations parked since the last flush
+    auto queue_of = [&](int q) -> uint32_t* { return q == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(q) * w.pool; };
+#endif
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += stride) {
         const uint32_t idx = base + uint32_t(lane);
         const bool valid = idx < n;
@@ -1213,12 +1228,24 @@ k_bin(TraceIO io, SceneView s, WaveBuffers w, RoundParams rp, int cur)
                 key = int(s.prim_mat_type[ph.prim]);
             }
         }
+#if ARTB_BIN_BATCH > 1
+        s_keys[n_parked][threadIdx.x] = key;
+        s_ids[n_parked][threadIdx.x] = id;
+        if (++n_parked == ARTB_BIN_BATCH) {
+            flush_batched_appends<ARTB_BIN_BATCH, ARTB_BIN_THREADS>(s_keys, s_ids, n_parked, Q_OUT_COUNT, &c->n_out[cur][0], queue_of, lane);
+            n_parked = 0;
+        }
+#else
         const uint32_t pos = multi_queue_reserve(key, &c->n_out[cur][key < 0 ? 0 : key], lane);
         if (key >= 0) {
             uint32_t* q = key == Q_REGEN ? w.q_regen[cur] : w.q_shade + size_t(key) * w.pool;
             q[pos] = id;
         }
+#endif
     }
+#if ARTB_BIN_BATCH > 1
+    if (n_parked) flush_batched_appends<ARTB_BIN_BATCH, ARTB_BIN_THREADS>(s_keys, s_ids, n_parked, Q_OUT_COUNT, &c->n_out[cur][0], queue_of, lane);
+#endif
 }
 
 // The one-phase walk: closest_hit() per ray, results appended to the same queues. all = 0: the rays k_finish found
